@@ -1,0 +1,152 @@
+// sha512.cuh — SHA-512 (FIPS 180-4) for the verify kernels and the Digest surface.
+//
+// Replaces: ed25519_dalek::Sha512 as used for k = H(R || A || M) inside Signature::verify / verify_batch
+// (crypto/src/lib.rs:200-219) and for Digest = SHA-512(..)[..32] at consensus/src/messages.rs:81,151,203,270,308
+// and mempool/src/processor.rs:30.
+//
+// One thread hashes one message (Merkle–Damgård is sequential within a message; parallelism is across
+// signatures / messages).  The 80 rounds are fully unrolled over a rolling 16-word schedule so every index
+// is a compile-time constant and the schedule lives in registers.
+#pragma once
+#include <cstdint>
+#include "fe.cuh"
+#include "hs_constants.cuh"
+
+#if defined(__CUDACC__)
+__device__ __constant__ uint64_t HS_SHA512_K_DEV[80] = {HS_SHA512_K_INIT};
+#endif
+
+HS_HD uint64_t sha_k(int i) {
+#if defined(__CUDA_ARCH__)
+  return HS_SHA512_K_DEV[i];
+#else
+  return HS_SHA512_K_HOST[i];
+#endif
+}
+
+HS_HD uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+HS_HD uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x0123);
+#else
+  return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
+#endif
+}
+// big-endian 64-bit message word from two little-endian 32-bit memory words (lo = bytes 0..3, hi = bytes 4..7)
+HS_HD uint64_t be64_from_le32(uint32_t lo, uint32_t hi) { return ((uint64_t)bswap32(lo) << 32) | bswap32(hi); }
+
+struct sha512_state {
+  uint64_t h[8];
+};
+
+HS_HD void sha512_init(sha512_state &s) {
+  const uint64_t h0[8] = {HS_SHA512_H0_INIT};
+  for (int i = 0; i < 8; i++) s.h[i] = h0[i];
+}
+
+// One compression; w[16] is consumed (used as the rolling schedule).
+HS_HD void sha512_compress(sha512_state &s, uint64_t (&w)[16]) {
+  uint64_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 80; i++) {
+    if (i >= 16) {
+      uint64_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+      uint64_t s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+      uint64_t s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+      w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+    }
+    uint64_t S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
+    uint64_t ch = (e & f) ^ (~e & g);
+    uint64_t t1 = h + S1 + ch + sha_k(i) + w[i & 15];
+    uint64_t S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
+    uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
+    uint64_t t2 = S0 + mj;
+    h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+  }
+  s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+
+// state -> 64 output bytes as 16 little-endian u32 words (word j = bytes 4j..4j+3 of the digest)
+HS_HD void sha512_output_words(const sha512_state &s, uint32_t (&out)[16]) {
+  for (int i = 0; i < 8; i++) {
+    out[2 * i] = bswap32((uint32_t)(s.h[i] >> 32));
+    out[2 * i + 1] = bswap32((uint32_t)s.h[i]);
+  }
+}
+
+// k-hash fast path: SHA-512(R[32] || A[32] || M[32]) — exactly one block (every message the reference signs is a
+// 32-byte Digest: crypto/src/lib.rs:185,200,206).  Inputs are little-endian u32 words as loaded from memory.
+HS_HD void sha512_ram32(uint32_t (&out)[16], const uint32_t (&R)[8], const uint32_t (&A)[8], const uint32_t (&M)[8]) {
+  uint64_t w[16];
+  for (int i = 0; i < 4; i++) {
+    w[i] = be64_from_le32(R[2 * i], R[2 * i + 1]);
+    w[4 + i] = be64_from_le32(A[2 * i], A[2 * i + 1]);
+    w[8 + i] = be64_from_le32(M[2 * i], M[2 * i + 1]);
+  }
+  w[12] = 0x8000000000000000ULL;
+  w[13] = 0;
+  w[14] = 0;
+  w[15] = 96 * 8;
+  sha512_state s;
+  sha512_init(s);
+  sha512_compress(s, w);
+  sha512_output_words(s, out);
+}
+
+// Byte-granular reader for arbitrary-length / arbitrarily-aligned messages.
+HS_HD uint64_t load_be64_bytes(const uint8_t *p) {
+  uint64_t v = 0;
+  for (int i = 0; i < 8; i++) v = (v << 8) | p[i];
+  return v;
+}
+
+// One 64-bit big-endian message word at message offset m (multiple of 8): real bytes, then the 0x80 terminator,
+// then zeros.  Keeps the schedule index static so w[] stays in registers.
+HS_HD uint64_t sha512_msg_word(const uint8_t *msg, uint64_t len, uint64_t m, bool aligned8) {
+  if (m + 8 <= len) {
+    if (aligned8) {
+      uint64_t le = *reinterpret_cast<const uint64_t *>(msg + m);
+      return ((uint64_t)bswap32((uint32_t)le) << 32) | bswap32((uint32_t)(le >> 32));
+    }
+    return load_be64_bytes(msg + m);
+  }
+  if (m > len) return 0;
+  uint64_t v = 0;
+  int nb = (int)(len - m);
+  for (int i = 0; i < nb; i++) v |= (uint64_t)msg[m + i] << (56 - 8 * i);
+  return v | ((uint64_t)0x80 << (56 - 8 * nb));
+}
+
+// General hash of prefix || msg[0..len): the prefix is n_prefix_words (0 or 8) big-endian 64-bit words already in
+// registers (R||A for the k-hash; none for Digest); message bytes stream from global memory.
+HS_HD void sha512_prefix_msg(uint32_t (&out)[16], const uint64_t (&prefix_words)[8], int n_prefix_words, const uint8_t *msg,
+                             uint64_t len) {
+  sha512_state s;
+  sha512_init(s);
+  const uint64_t P = (uint64_t)n_prefix_words * 8;
+  const uint64_t total = P + len;
+  const uint64_t nblk = (total + 17 + 127) / 128;
+  const bool aligned8 = ((reinterpret_cast<uintptr_t>(msg) & 7u) == 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (uint64_t b = 0; b < nblk; b++) {
+    uint64_t w[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; j++) {
+      uint64_t o = b * 128 + 8 * (uint64_t)j;
+      uint64_t v;
+      if (o < P) v = prefix_words[j & 7];  // only reachable for b == 0, j < 8
+      else v = sha512_msg_word(msg, len, o - P, aligned8);
+      if (b == nblk - 1 && j == 14) v = total >> 61;
+      if (b == nblk - 1 && j == 15) v = total << 3;
+      w[j] = v;
+    }
+    sha512_compress(s, w);
+  }
+  sha512_output_words(s, out);
+}

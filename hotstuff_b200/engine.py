@@ -1,0 +1,154 @@
+"""Engine: Python handle on one hs_ctx (one CUDA device).  Thin: marshals numpy / torch buffers into the C ABI.
+
+Host-side mirror of the reference interface lives in crypto.py; this module is the batch surface the consensus call
+sites would use (QC/TC vote sets, mempool batch digests) plus device-resident entry points for the benchmark.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+MODE_STRICT = 0    # Signature::verify      (crypto/src/lib.rs:200-204)
+MODE_BATCH_EQ = 1  # Signature::verify_batch (crypto/src/lib.rs:206-219), per-signature condition
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _u8(a, shape_last=None):
+    a = np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray, memoryview)) else a, dtype=np.uint8)
+    if shape_last is not None and a.size % shape_last:
+        raise ValueError("buffer length is not a multiple of %d" % shape_last)
+    return a
+
+
+def bitmap_to_bools(bitmap, n):
+    return np.unpackbits(bitmap.view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.hs_ctx_create(ctypes.byref(h), int(device), 0)
+        if rc != 0 or not h:
+            raise EngineError("hs_ctx_create(device=%d) failed with status %d (no GPU / CUDA error); there is no CPU fallback" % (device, rc))
+        self.h = h
+        self.device = int(device)
+        self.n_keys = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed: status %d: %s" % (what, rc, self.lib.hs_last_error(self.h).decode()))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.hs_kernel_launches(self.h))
+
+    # ---- host-buffer API -------------------------------------------------------------------------------------
+    def verify_rec128(self, recs, mode=MODE_STRICT):
+        """recs: (n,128) uint8 [sig64|pk32|msg32] -> bool[n]"""
+        recs = _u8(recs, 128).reshape(-1, 128)
+        n = recs.shape[0]
+        bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.hs_verify_rec128(self.h, _ptr(recs), n, mode, _ptr(bm)), "hs_verify_rec128")
+        return bitmap_to_bools(bm, n)
+
+    def verify_strict_batch(self, recs):
+        recs = _u8(recs, 128).reshape(-1, 128)
+        n = recs.shape[0]
+        bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.hs_verify_strict_batch(self.h, _ptr(recs), n, _ptr(bm)), "hs_verify_strict_batch")
+        return bitmap_to_bools(bm, n)
+
+    def verify_var(self, sig, pk, msgs, off, mode=MODE_STRICT):
+        sig = _u8(sig, 64).reshape(-1, 64)
+        pk = _u8(pk, 32).reshape(-1, 32)
+        n = sig.shape[0]
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        assert pk.shape[0] == n and off.shape[0] == n + 1
+        msgs = _u8(msgs)
+        bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.hs_verify_var(self.h, _ptr(sig), _ptr(pk), _ptr(msgs) if msgs.size else None, _ptr(off), n, mode, _ptr(bm)),
+                    "hs_verify_var")
+        return bitmap_to_bools(bm, n)
+
+    def verify_batch_shared_msg(self, digest, votes, want_bitmap=False):
+        """votes: (n,96) uint8 [pk32|sig64].  Returns all_ok (and bool[n] when want_bitmap)."""
+        digest = _u8(digest)
+        assert digest.size == 32
+        votes = _u8(votes, 96).reshape(-1, 96)
+        n = votes.shape[0]
+        ok = ctypes.c_int(0)
+        bm = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32) if want_bitmap else None
+        self._check(self.lib.hs_verify_batch_shared_msg(self.h, _ptr(digest), _ptr(votes) if n else None, n, ctypes.byref(ok), _ptr(bm)),
+                    "hs_verify_batch_shared_msg")
+        return (bool(ok.value), bitmap_to_bools(bm, n)) if want_bitmap else bool(ok.value)
+
+    def committee_register(self, pks):
+        pks = _u8(pks, 32).reshape(-1, 32)
+        n = pks.shape[0]
+        bm = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32)
+        self._check(self.lib.hs_committee_register(self.h, _ptr(pks) if n else None, n, _ptr(bm)), "hs_committee_register")
+        self.n_keys = n
+        return bitmap_to_bools(bm, n)
+
+    def verify_committee(self, validator_idx, sig, digests, msg_idx=None, mode=MODE_STRICT):
+        vidx = np.ascontiguousarray(validator_idx, dtype=np.uint32)
+        sig = _u8(sig, 64).reshape(-1, 64)
+        digests = _u8(digests, 32).reshape(-1, 32)
+        n = sig.shape[0]
+        assert vidx.shape[0] == n
+        midx = None if msg_idx is None else np.ascontiguousarray(msg_idx, dtype=np.uint32)
+        bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.hs_verify_committee(self.h, _ptr(vidx), _ptr(sig), _ptr(midx), _ptr(digests), digests.shape[0], n, mode, _ptr(bm)),
+                    "hs_verify_committee")
+        return bitmap_to_bools(bm, n)
+
+    def digest32_batch(self, data, off):
+        data = _u8(data)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = off.shape[0] - 1
+        out = np.zeros((n, 32), dtype=np.uint8)
+        self._check(self.lib.hs_digest32_batch(self.h, _ptr(data) if data.size else None, _ptr(off), n, _ptr(out)), "hs_digest32_batch")
+        return out
+
+    # ---- device-resident API (torch tensors on this engine's device; enqueued on torch's current stream) -------
+    @staticmethod
+    def _stream():
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def verify_rec128_dev(self, d_recs, d_bitmap, n, mode=MODE_STRICT):
+        self._check(self.lib.hs_verify_rec128_dev(self.h, d_recs.data_ptr(), n, mode, d_bitmap.data_ptr(), self._stream()), "hs_verify_rec128_dev")
+
+    def verify_var_dev(self, d_sig, d_pk, d_msgs, d_off, d_bitmap, n, mode=MODE_STRICT):
+        self._check(self.lib.hs_verify_var_dev(self.h, d_sig.data_ptr(), d_pk.data_ptr(), d_msgs.data_ptr(), d_off.data_ptr(), n, mode,
+                                               d_bitmap.data_ptr(), self._stream()), "hs_verify_var_dev")
+
+    def verify_committee_dev(self, d_vidx, d_sig, d_digests, d_bitmap, n, d_midx=None, mode=MODE_STRICT):
+        self._check(self.lib.hs_verify_committee_dev(self.h, d_vidx.data_ptr(), d_sig.data_ptr(), None if d_midx is None else d_midx.data_ptr(),
+                                                     d_digests.data_ptr(), n, mode, d_bitmap.data_ptr(), self._stream()),
+                    "hs_verify_committee_dev")
+
+    def digest32_dev(self, d_data, d_off, d_out, n):
+        self._check(self.lib.hs_digest32_dev(self.h, d_data.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), self._stream()), "hs_digest32_dev")

@@ -1,0 +1,102 @@
+/*
+ * hs_crypto.h — C ABI of the B200 batch Ed25519 verification / SHA-512 digest engine.
+ *
+ * This is the drop-in boundary for ONE path of asonnino/hotstuff: the `crypto` crate's verify / verify_batch /
+ * Digest surface.  The reference has no FFI today (it calls ed25519-dalek directly, crypto/Cargo.toml:10); each
+ * entry point below names the reference interface it replaces (paths relative to the reference repo root).
+ * INTEGRATION.md shows the Rust `extern "C"` binding a maintainer would add to crypto/src/lib.rs.
+ *
+ * Conventions
+ *   - Every function returns 0 (HS_OK) when the engine ran; verdicts are in the output buffers.  Non-zero = engine
+ *     failure (CUDA error, bad argument): the caller must treat every signature of that call as REJECTED
+ *     (reference behaviour: any Err drops the message, consensus/src/core.rs:434-439).  There is no CPU fallback.
+ *   - Malformed inputs (S >= l, non-decompressible A or R, ...) are verdict 0, never an error.
+ *   - Host-pointer entry points copy inputs to the device, run, and copy results back before returning; nothing is
+ *     retained.  `_dev` entry points take device pointers and a cudaStream_t (as void*) and return after enqueueing.
+ *   - A context is bound to one CUDA device and is thread-safe (calls are serialised on an internal mutex).
+ *   - Bitmaps: bit (i & 31) of word (i >> 5) is the verdict of item i; unused high bits of the last word are 0.
+ */
+#ifndef HS_CRYPTO_H
+#define HS_CRYPTO_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_OK 0
+#define HS_ERR_CUDA 1
+#define HS_ERR_ARG 2
+#define HS_ERR_NOMEM 3
+
+/* verdict selector for the verify entry points */
+#define HS_MODE_STRICT 0u /* Signature::verify semantics  = dalek verify_strict          (crypto/src/lib.rs:200-204) */
+#define HS_MODE_BATCH_EQ 1u /* per-signature condition of Signature::verify_batch          (crypto/src/lib.rs:206-219) */
+
+typedef struct hs_ctx hs_ctx;
+
+/* One (Signature, PublicKey, Digest) triple exactly as Signature::verify receives it:
+ * sig = part1 || part2 (crypto/src/lib.rs:179-182,193-198), pk = PublicKey.0 (:66), msg = Digest.0 (:22). */
+typedef struct {
+  uint8_t sig[64];
+  uint8_t pk[32];
+  uint8_t msg[32];
+} hs_rec128;
+
+/* One QC vote = (PublicKey, Signature), consensus/src/messages.rs:168 `votes: Vec<(PublicKey, Signature)>`. */
+typedef struct {
+  uint8_t pk[32];
+  uint8_t sig[64];
+} hs_vote;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+/* device: CUDA ordinal.  Builds the base-point table on the GPU.  flags: reserved, pass 0. */
+int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
+void hs_ctx_destroy(hs_ctx *ctx);
+/* Human-readable description of the last failure on this context (never NULL). */
+const char *hs_last_error(const hs_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t hs_kernel_launches(const hs_ctx *ctx);
+/* Pinned host memory helpers (optional; any host pointer is accepted by the host entry points). */
+void *hs_host_alloc(size_t bytes);
+void hs_host_free(void *p);
+
+/* ---- Signature::verify (crypto/src/lib.rs:200-204), n independent triples -------------------------------------- */
+/* Callers: Block::verify consensus/src/messages.rs:64, Vote::verify :144, Timeout::verify :258, TC::verify :312. */
+int hs_verify_strict_batch(hs_ctx *ctx, const hs_rec128 *recs, size_t n, uint32_t *out_bitmap);
+/* Same with an explicit verdict mode (HS_MODE_*). */
+int hs_verify_rec128(hs_ctx *ctx, const hs_rec128 *recs, size_t n, uint32_t mode, uint32_t *out_bitmap);
+/* Variable-length messages (PureEdDSA over the raw bytes): sig[n][64], pk[n][32], msgs concatenated, off[n+1]. */
+int hs_verify_var(hs_ctx *ctx, const uint8_t *sig, const uint8_t *pk, const uint8_t *msgs, const uint64_t *off, size_t n,
+                  uint32_t mode, uint32_t *out_bitmap);
+
+/* ---- Signature::verify_batch (crypto/src/lib.rs:206-219): one digest, n votes ---------------------------------- */
+/* Caller: QC::verify consensus/src/messages.rs:197.  *all_ok = 1 iff every vote parses and satisfies the
+ * cofactorless equation (deterministic restatement of dalek::verify_batch). */
+int hs_verify_batch_shared_msg(hs_ctx *ctx, const uint8_t digest[32], const hs_vote *votes, size_t n, int *all_ok,
+                               uint32_t *out_bitmap_or_null);
+
+/* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
+/* Decompresses every key and builds its comb table in HBM (384 KB per key).  out_valid_bitmap (nullable): bit i = key i
+ * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
+int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
+/* Vote i is (validator_idx[i], sig[i]) over digests[msg_idx[i]].  msg_idx may be NULL when n_msgs == 1. */
+int hs_verify_committee(hs_ctx *ctx, const uint32_t *validator_idx, const uint8_t *sig /* n x 64 */, const uint32_t *msg_idx,
+                        const uint8_t *digests /* n_msgs x 32 */, size_t n_msgs, size_t n, uint32_t mode, uint32_t *out_bitmap);
+
+/* ---- Digest surface: out[i] = SHA-512(data[off[i] .. off[i+1]))[0..32] ------------------------------------------ */
+/* Replaces Sha512::digest(..)[..32] at mempool/src/processor.rs:30 and consensus/src/messages.rs:81,151,203,270,308. */
+int hs_digest32_batch(hs_ctx *ctx, const uint8_t *data, const uint64_t *off, size_t n, uint8_t *out /* n x 32 */);
+
+/* ---- device-resident entry points (inputs already in HBM; enqueue on `stream`, a cudaStream_t) ------------------- */
+int hs_verify_rec128_dev(hs_ctx *ctx, const void *d_recs, size_t n, uint32_t mode, void *d_bitmap, void *stream);
+int hs_verify_var_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk, const void *d_msgs, const void *d_off, size_t n,
+                      uint32_t mode, void *d_bitmap, void *stream);
+int hs_verify_committee_dev(hs_ctx *ctx, const void *d_validator_idx, const void *d_sig, const void *d_msg_idx,
+                            const void *d_digests, size_t n, uint32_t mode, void *d_bitmap, void *stream);
+int hs_digest32_dev(hs_ctx *ctx, const void *d_data, const void *d_off, size_t n, void *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -323,6 +323,29 @@ static int sc_is_canonical(const uint8_t s[32]) {
   return !limbs_geq(x, HS_SC_L_64, 4);
 }
 
+/* ------------------------------------------------------------------ fixed-base [s]B for input synthesis */
+/* radix-16 unsigned comb: g_comb[i][j] = j * 16^i * B.  Only keygen/sign use it (bulk fixture generation);
+ * tests check it against ge_scalarmult_simple. */
+static ge g_comb[64][16];
+static pthread_once_t g_comb_once = PTHREAD_ONCE_INIT;
+static void comb_init(void) {
+  ge base; ge_base(&base);
+  for (int i = 0; i < 64; i++) {
+    ge_identity(&g_comb[i][0]);
+    for (int j = 1; j < 16; j++) ge_add(&g_comb[i][j], &g_comb[i][j - 1], &base);
+    for (int k = 0; k < 4; k++) ge_dbl(&base, &base);
+  }
+}
+static void ge_scalarmult_base(ge *r, const uint8_t sc[32]) {
+  pthread_once(&g_comb_once, comb_init);
+  ge acc; ge_identity(&acc);
+  for (int i = 0; i < 64; i++) {
+    int nib = (sc[i >> 1] >> ((i & 1) * 4)) & 15;
+    if (nib) ge_add(&acc, &acc, &g_comb[i][nib]);
+  }
+  *r = acc;
+}
+
 /* ------------------------------------------------------------------ keygen / sign (RFC 8032 §5.1.5-5.1.6) */
 static void expand_seed(const uint8_t seed[32], uint8_t a[32], uint8_t prefix[32]) {
   uint8_t h[64]; hso_sha512(seed, 32, h);
@@ -331,15 +354,18 @@ static void expand_seed(const uint8_t seed[32], uint8_t a[32], uint8_t prefix[32
 }
 void hso_keygen(const uint8_t seed[32], uint8_t pk[32]) {
   uint8_t a[32], prefix[32]; ge B, A; expand_seed(seed, a, prefix);
-  ge_base(&B); ge_scalarmult_simple(&A, a, &B); ge_compress(pk, &A);
+  (void)B; ge_scalarmult_base(&A, a); ge_compress(pk, &A);
 }
+static void sign_with_pk(const uint8_t seed[32], const uint8_t pk[32], const uint8_t *msg, size_t len, uint8_t sig[64]);
 void hso_sign(const uint8_t seed[32], const uint8_t *msg, size_t len, uint8_t sig[64]) {
-  uint8_t a[32], prefix[32], pk[32], h[64], r[32], k[32]; ge B, P; sha512_ctx c;
-  expand_seed(seed, a, prefix); ge_base(&B);
-  ge_scalarmult_simple(&P, a, &B); ge_compress(pk, &P);
+  uint8_t pk[32]; hso_keygen(seed, pk); sign_with_pk(seed, pk, msg, len, sig);
+}
+static void sign_with_pk(const uint8_t seed[32], const uint8_t pk[32], const uint8_t *msg, size_t len, uint8_t sig[64]) {
+  uint8_t a[32], prefix[32], h[64], r[32], k[32]; ge P; sha512_ctx c;
+  expand_seed(seed, a, prefix);
   sha512_init(&c); sha512_update(&c, prefix, 32); sha512_update(&c, msg, len); sha512_final(&c, h);
   hso_sc_reduce64(h, r);
-  ge_scalarmult_simple(&P, r, &B); ge_compress(sig, &P);
+  ge_scalarmult_base(&P, r); ge_compress(sig, &P);
   sha512_init(&c); sha512_update(&c, sig, 32); sha512_update(&c, pk, 32); sha512_update(&c, msg, len); sha512_final(&c, h);
   hso_sc_reduce64(h, k);
   hso_sc_muladd(k, a, r, sig + 32);
@@ -488,6 +514,35 @@ int hso_verify_batch_shared_msg(const uint8_t digest[32], const uint8_t *votes, 
   if (!bitmap_or_null) free(bm);
   return all;
 }
+
+/* bulk signing for fixture / benchmark-input synthesis: item i signs msgs[off[i]..off[i+1]) with key key_idx[i] */
+typedef struct { const uint8_t *seeds, *pks, *msgs; const uint32_t *key_idx; const uint64_t *off; uint8_t *sigs; size_t lo, hi; } sjob_t;
+static void *sjob_run(void *arg) {
+  sjob_t *j = (sjob_t *)arg;
+  for (size_t i = j->lo; i < j->hi; i++) {
+    uint32_t k = j->key_idx[i];
+    sign_with_pk(j->seeds + 32 * (size_t)k, j->pks + 32 * (size_t)k, j->msgs + j->off[i], (size_t)(j->off[i + 1] - j->off[i]), j->sigs + 64 * i);
+  }
+  return NULL;
+}
+void hso_sign_batch(const uint8_t *seeds, const uint8_t *pks, const uint32_t *key_idx, const uint8_t *msgs, const uint64_t *off,
+                    size_t n, int nthreads, uint8_t *sigs) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_once(&g_comb_once, comb_init);
+  pthread_t th[256]; sjob_t jobs[256]; int started = 0; size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    size_t lo = (size_t)t * per, hi = lo + per; if (lo >= n) break; if (hi > n) hi = n;
+    jobs[t] = (sjob_t){seeds, pks, msgs, key_idx, off, sigs, lo, hi};
+    if (nthreads == 1) sjob_run(&jobs[t]); else pthread_create(&th[t], NULL, sjob_run, &jobs[t]);
+    started++;
+  }
+  if (nthreads > 1) for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
+void hso_keygen_batch(const uint8_t *seeds, size_t n, uint8_t *pks) { for (size_t i = 0; i < n; i++) hso_keygen(seeds + 32 * i, pks + 32 * i); }
+/* [s]B through the slow double-and-add, for checking the comb used by keygen/sign */
+void hso_scalarmult_base_simple(const uint8_t sc[32], uint8_t out[32]) { ge B, r; ge_base(&B); ge_scalarmult_simple(&r, sc, &B); ge_compress(out, &r); }
+void hso_scalarmult_base_comb(const uint8_t sc[32], uint8_t out[32]) { ge r; ge_scalarmult_base(&r, sc); ge_compress(out, &r); }
 
 /* ------------------------------------------------------------------ fixture helpers */
 int hso_point_decompress_ok(const uint8_t enc[32]) { ge p; return ge_decompress(&p, enc); }

@@ -30,6 +30,13 @@ void hso_keygen(const uint8_t seed[32], uint8_t pk[32]);
 /* RFC 8032 5.1.6 / dalek Keypair::sign (crypto/src/lib.rs:185-191). */
 void hso_sign(const uint8_t seed[32], const uint8_t *msg, size_t len, uint8_t sig[64]);
 
+/* Bulk input synthesis (fixtures, benchmark inputs): item i signs msgs[off[i]..off[i+1]) with key key_idx[i]. */
+void hso_keygen_batch(const uint8_t *seeds, size_t n, uint8_t *pks);
+void hso_sign_batch(const uint8_t *seeds, const uint8_t *pks, const uint32_t *key_idx, const uint8_t *msgs, const uint64_t *off,
+                    size_t n, int nthreads, uint8_t *sigs);
+void hso_scalarmult_base_simple(const uint8_t sc[32], uint8_t out[32]);
+void hso_scalarmult_base_comb(const uint8_t sc[32], uint8_t out[32]);
+
 /* Per-signature decision bits. */
 #define HSO_PARSE_OK 1u   /* S < l, A decompresses (Signature::from_bytes + PublicKey::from_bytes, lib.rs:201-202) */
 #define HSO_R_OK 2u       /* R decompresses */

@@ -1,0 +1,132 @@
+// hostemu.cpp — TEST-ONLY host build of the device headers (HS_HOST_EMU): the exact curve / scalar / window /
+// table logic of the CUDA kernels compiled by g++ with the PTX field primitives swapped for portable C, so it can
+// be checked against the oracle on a machine without a GPU.  Never linked into the product library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../hotstuff_b200/csrc/verify_core.cuh"
+
+static std::vector<ge_niels> g_btable;
+static void ensure_btable() {
+  if (!g_btable.empty()) return;
+  g_btable.resize(HS_COMB_TABLE_NIELS);
+  ge_ext B;
+  ge_basepoint(B);
+  for (int w = 0; w < HS_COMB_WINDOWS; w++) comb_build_window(g_btable.data(), B, w);
+}
+static void load_words(uint32_t (&w)[8], const uint8_t *p) { memcpy(w, p, 32); }
+
+extern "C" {
+void emu_fe_op(int op, const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) {
+  fe x, y, r;
+  memcpy(x.v, a, 32);
+  memcpy(y.v, b, 32);
+  switch (op) {
+    case 0: fe_mul(r, x, y); break;
+    case 1: fe_sqr(r, x); break;
+    case 2: fe_add(r, x, y); break;
+    case 3: fe_sub(r, x, y); break;
+    case 4: fe_canon(r, x); break;
+    case 5: fe_invert(r, x); break;
+    case 6: fe_pow_p58(r, x); break;
+    case 7: fe_neg(r, x); break;
+    default: fe_set0(r);
+  }
+  memcpy(out, r.v, 32);
+}
+void emu_sc_reduce512(const uint8_t in[64], uint8_t out[32]) {
+  uint32_t x[16], r[8];
+  memcpy(x, in, 64);
+  sc_reduce512(r, x);
+  memcpy(out, r, 32);
+}
+int emu_sc_is_canonical(const uint8_t s[32]) {
+  uint32_t w[8];
+  load_words(w, s);
+  return (int)sc_is_canonical(w);
+}
+// digits of the signed recoding, W in {4, 8}; returns count
+int emu_sc_digits(int W, int msb, const uint8_t s[32], int *out) {
+  uint32_t w[8];
+  load_words(w, s);
+  if (W == 8) { digits_lsb<8> d; d.init(w); for (int i = 0; i < 32; i++) out[i] = d.next(); return 32; }
+  if (W == 4 && msb) { digits_msb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[63 - i] = d.next(); return 64; }
+  if (W == 4) { digits_lsb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[i] = d.next(); return 64; }
+  return 0;
+}
+void emu_sha512(const uint8_t *msg, uint64_t len, uint8_t out[64]) {
+  uint32_t o[16];
+  uint64_t pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  sha512_prefix_msg(o, pre, 0, msg, len);
+  memcpy(out, o, 64);
+}
+void emu_sha512_ram(const uint8_t R[32], const uint8_t A[32], const uint8_t *msg, uint64_t len, uint8_t out[64]) {
+  uint32_t o[16], r[8], a[8];
+  load_words(r, R);
+  load_words(a, A);
+  if (len == 32) {
+    uint32_t m[8];
+    load_words(m, msg);
+    sha512_ram32(o, r, a, m);
+  } else {
+    uint64_t pre[8];
+    for (int i = 0; i < 4; i++) { pre[i] = be64_from_le32(r[2 * i], r[2 * i + 1]); pre[4 + i] = be64_from_le32(a[2 * i], a[2 * i + 1]); }
+    sha512_prefix_msg(o, pre, 8, msg, len);
+  }
+  memcpy(out, o, 64);
+}
+int emu_decompress(const uint8_t enc[32], uint8_t x_out[32], uint8_t y_out[32]) {
+  uint32_t w[8];
+  load_words(w, enc);
+  ge_ext p;
+  uint32_t ok = ge_decompress(p, w);
+  fe cx, cy;
+  fe_canon(cx, p.X);
+  fe_canon(cy, p.Y);
+  memcpy(x_out, cx.v, 32);
+  memcpy(y_out, cy.v, 32);
+  return (int)ok;
+}
+int emu_enc_is_small_order(const uint8_t enc[32]) {
+  uint32_t w[8];
+  load_words(w, enc);
+  return (int)ge_enc_is_small_order(w);
+}
+// generic-key verify of one (sig, pk, msg); returns HS_F_* flags
+unsigned emu_verify_generic(const uint8_t sig[64], const uint8_t pk[32], const uint8_t *msg, uint64_t len) {
+  ensure_btable();
+  uint32_t R[8], S[8], A[8], h[16];
+  load_words(R, sig);
+  load_words(S, sig + 32);
+  load_words(A, pk);
+  uint8_t hb[64];
+  emu_sha512_ram(sig, pk, msg, len, hb);
+  memcpy(h, hb, 64);
+  ge_cached tab[9];
+  return verify_generic_core(R, S, A, h, g_btable.data(), tab);
+}
+// committee path: builds -A's comb table on the fly (slow; tests only)
+unsigned emu_verify_committee(const uint8_t sig[64], const uint8_t pk[32], const uint8_t *msg, uint64_t len) {
+  ensure_btable();
+  uint32_t R[8], S[8], A[8], h[16];
+  load_words(R, sig);
+  load_words(S, sig + 32);
+  load_words(A, pk);
+  ge_ext Apt, negA;
+  uint32_t a_ok = ge_decompress(Apt, A);
+  uint32_t a_small = ge_enc_is_small_order(A);
+  ge_neg(negA, Apt);
+  std::vector<ge_niels> at(HS_COMB_TABLE_NIELS);
+  if (a_ok) for (int w = 0; w < HS_COMB_WINDOWS; w++) comb_build_window(at.data(), negA, w);
+  else for (auto &q : at) ge_niels_identity(q);
+  uint8_t hb[64];
+  emu_sha512_ram(sig, pk, msg, len, hb);
+  memcpy(h, hb, 64);
+  return verify_committee_core(R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1));
+}
+const uint8_t *emu_btable_bytes(uint64_t *nbytes) {
+  ensure_btable();
+  *nbytes = g_btable.size() * sizeof(ge_niels);
+  return reinterpret_cast<const uint8_t *>(g_btable.data());
+}
+}

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle (the parity reference) against everything independent we have: FIPS 180-4 / hashlib, RFC 8032
+§7.1 known answers, OpenSSL and libsodium on random inputs, and the fixtures derived from the reference's own tests
+(crypto/src/tests/crypto_tests.rs, consensus/src/tests/common.rs, mempool/src/tests/common.rs)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle_api import EQ_OK, PARSE_OK, R_OK, SMALL, STRICT, make_workload, to_rec128
+
+VALID = PARSE_OK | R_OK | EQ_OK | STRICT
+
+
+def test_sha512_matches_hashlib(oracle):
+    rng = np.random.default_rng(0)
+    for ln in list(range(0, 300)) + [511, 512, 513, 1000, 4096, 15000]:
+        m = rng.integers(0, 256, ln, dtype=np.uint8).tobytes()
+        assert oracle.sha512(m) == hashlib.sha512(m).digest()
+
+
+def test_digest_kats(oracle, golden):
+    for k in golden["digest_kats"]:
+        m = bytes.fromhex(k["msg"])
+        assert oracle.sha512(m).hex() == k["sha512"]
+        assert oracle.digest32(m).hex() == k["sha512"][:64]
+
+
+def test_rfc8032_known_answers(oracle, golden):
+    assert len(golden["rfc8032"]) >= 3
+    for v in golden["rfc8032"]:
+        sk, pk, msg, sig = (bytes.fromhex(v[k]) for k in ("sk", "pk", "msg", "sig"))
+        assert oracle.keygen(sk) == pk
+        assert oracle.sign(sk, msg) == sig
+        assert oracle.flags(sig, pk, msg) == VALID
+        assert oracle.flags(sig, pk, msg, fast=True) == VALID
+
+
+def test_reference_fixtures(oracle, golden):
+    """keys() / Hello-world signature / qc() votes / batch_digest() of the reference's test suites."""
+    r = golden["reference"]
+    seeds = [bytes.fromhex(s) for s in r["seeds"]]
+    pks = [bytes.fromhex(s) for s in r["pks"]]
+    for s, p in zip(seeds, pks):
+        assert oracle.keygen(s) == p
+    hello = oracle.digest32(b"Hello, world!")
+    assert hello.hex() == r["hello_digest"]
+    sig = oracle.sign(seeds[3], hello)
+    assert sig.hex() == r["hello_sig_key3"]
+    assert oracle.verify_strict(sig, pks[3], hello)                                   # crypto_tests.rs:50-61
+    assert not oracle.verify_strict(sig, pks[3], oracle.digest32(b"Bad message!"))    # crypto_tests.rs:64-77
+    # verify_valid_batch / verify_invalid_batch (crypto_tests.rs:80-115)
+    votes = b"".join(pks[i] + oracle.sign(seeds[i], hello) for i in (3, 2, 1))
+    assert oracle.verify_batch_shared_msg(hello, np.frombuffer(votes, np.uint8))[0]
+    bad = b"".join(pks[i] + oracle.sign(seeds[i], hello) for i in (3, 2)) + pks[1] + bytes(64)
+    assert not oracle.verify_batch_shared_msg(hello, np.frombuffer(bad, np.uint8))[0]
+    # qc() fixture (consensus/src/tests/common.rs:129-144, messages_tests.rs:8-10)
+    qcd = oracle.digest32(bytes(32) + (1).to_bytes(8, "little"))
+    assert qcd.hex() == r["qc_digest"]
+    qv = b"".join(bytes.fromhex(v["pk"]) + bytes.fromhex(v["sig"]) for v in r["qc_votes"])
+    assert oracle.verify_batch_shared_msg(qcd, np.frombuffer(qv, np.uint8))[0]
+    # mempool batch_digest() (mempool/src/tests/common.rs:65-77, processor_tests.rs:8-38)
+    assert oracle.digest32(bytes.fromhex(r["serialized_batch"])).hex() == r["batch_digest"]
+
+
+def test_golden_vectors_reproduce(oracle, golden):
+    for v in golden["vectors"]:
+        sig, pk, msg = bytes.fromhex(v["sig"]), bytes.fromhex(v["pk"]), bytes.fromhex(v["msg"])
+        assert oracle.flags(sig, pk, msg) == v["flags"], v["name"]
+        assert oracle.flags(sig, pk, msg, fast=True) == v["flags"], v["name"]
+        if "independent" in v:
+            assert v["strict"] == v["independent"] == v["openssl"] == v["libsodium"], v["name"]
+
+
+def test_cross_check_openssl_and_libsodium(oracle):
+    """Random valid and plainly-corrupted signatures: all three implementations must agree."""
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    from cryptography.hazmat.primitives import serialization
+    import nacl.bindings
+    rng = np.random.default_rng(5)
+    for i in range(150):
+        seed = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+        m = rng.integers(0, 256, int(rng.integers(0, 200)), dtype=np.uint8).tobytes()
+        k = Ed25519PrivateKey.from_private_bytes(seed)
+        pk = k.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
+        assert oracle.keygen(seed) == pk
+        sig = oracle.sign(seed, m)
+        assert sig == k.sign(m)
+        assert nacl.bindings.crypto_sign_open(sig + m, pk) == m
+        assert oracle.flags(sig, pk, m) == VALID
+        bad = bytearray(sig + m)
+        pos = int(rng.integers(0, len(bad) * 8))
+        bad[pos >> 3] ^= 1 << (pos & 7)
+        bsig, bm = bytes(bad[:64]), bytes(bad[64:])
+        try:
+            nacl.bindings.crypto_sign_open(bsig + bm, pk)
+            sodium_ok = True
+        except Exception:
+            sodium_ok = False
+        assert oracle.verify_strict(bsig, pk, bm) == sodium_ok is False
+
+
+def test_small_order_equivalence(oracle, golden):
+    """The 14 torsion encodings are exactly the decompressible encodings with [8]P == identity among the candidates
+    (all y in {0..40} and {p-40..2^255-1} with both sign bits) — backs the byte-level blocklist used on the GPU."""
+    P = 2**255 - 19
+    tors = set(golden["torsion_encodings"])
+    assert len(tors) == 14
+    for t in tors:
+        assert oracle.is_small_order(bytes.fromhex(t)) == 1
+    cands = list(range(0, 41)) + list(range(P - 40, 2**255))
+    for y in cands:
+        for sign in (0, 1):
+            enc = bytearray(int(y).to_bytes(32, "little"))
+            enc[31] |= sign << 7
+            so = oracle.is_small_order(bytes(enc))
+            assert (so == 1) == (bytes(enc).hex() in tors), (y, sign, so)
+
+
+def test_config1_plumbing_cpu(oracle):
+    """BASELINE config 1: verify_batch of 1,024 synthetic (sig, pk, 32 B msg) on the CPU path."""
+    w = make_workload(oracle, 1024, n_keys=1024, seed=11)
+    recs = to_rec128(w)
+    assert oracle.verify_rec128(recs).all()
+    recs[517, 13] ^= 0x04
+    got = oracle.verify_rec128(recs)
+    assert not got[517] and got.sum() == 1023
+    # shared-message form (Signature::verify_batch shape): one digest, 1,024 signers
+    digest = oracle.digest32(b"config-1 shared digest")
+    msgs = np.tile(np.frombuffer(digest, np.uint8), 1024)
+    off = np.arange(1025, dtype=np.uint64) * 32
+    sig = oracle.sign_batch(w["seeds"], w["pks"], np.arange(1024, dtype=np.uint32), msgs, off)
+    votes = np.concatenate([w["pks"], sig], axis=1)
+    ok, bits = oracle.verify_batch_shared_msg(digest, votes, nthreads=8)
+    assert ok and bits.all()
+    votes[700, 40] ^= 1
+    ok, bits = oracle.verify_batch_shared_msg(digest, votes, nthreads=8)
+    assert not ok and not bits[700] and bits.sum() == 1023
+
+
+def test_multithreaded_batch_matches_single(oracle):
+    w = make_workload(oracle, 333, n_keys=7, seed=3, corrupt_frac=0.1)
+    recs = to_rec128(w)
+    a = oracle.verify_rec128(recs, nthreads=1)
+    b = oracle.verify_rec128(recs, nthreads=8)
+    assert (a == b).all() and (~a).sum() >= 1
+    assert (a[~w["corrupted"]]).all()

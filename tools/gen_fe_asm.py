@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""Generate the inline-PTX field multiplication / squaring for GF(2^255-19) on sm_100a.
+
+Representation: 8 saturated 32-bit limbs, value in [0, 2^256), congruent mod p = 2^255-19
+(2^256 = 38 mod p).  The schoolbook products are laid out as `mad.lo.cc.u32` / `madc.hi.cc.u32`
+pairs on two interleaved accumulator arrays (even / odd columns) so that ptxas fuses every pair into a
+single `IMAD.WIDE.U32.X Rd, Pc, Ra, Rb, Rd, Pc` (64-bit multiply-accumulate with carry-in/out) — measured
+on B200 at ~52 lane-ops/clk/SM, i.e. one SASS instruction per 32x32 partial product and no separate
+carry handling (tools/microbench/pipes.cu, profiles/r01_pipes.txt).
+
+The generator builds an abstract instruction list, *simulates it in Python against big-integer
+arithmetic* (random + all-ones + edge inputs) and only then emits PTX, so a lost carry cannot reach the GPU.
+
+Output: hotstuff_b200/csrc/fe_asm.cuh
+"""
+import os
+import random
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+M32 = (1 << 32) - 1
+P = 2**255 - 19
+
+
+class Prog:
+    def __init__(self):
+        self.ops = []          # (mnemonic, dst, [srcs])  srcs are reg names or ints
+        self.tmp = set()
+
+    def emit(self, op, dst, *srcs):
+        self.ops.append((op, dst, list(srcs)))
+
+    # ---- simulation -----------------------------------------------------
+    def run(self, env):
+        cc = 0
+        env = dict(env)
+
+        def val(x):
+            return x if isinstance(x, int) else env[x]
+
+        for op, dst, srcs in self.ops:
+            s = [val(x) for x in srcs]
+            base = op.replace(".u32", "")
+            if base in ("mul.lo", "mul.hi"):
+                pr = s[0] * s[1]
+                env[dst] = (pr & M32) if base == "mul.lo" else (pr >> 32)
+                continue
+            if base == "shf.l":
+                env[dst] = ((s[1] << s[2]) | (s[0] >> (32 - s[2]))) & M32
+                continue
+            if base == "and":
+                env[dst] = s[0] & s[1]
+                continue
+            parts = base.split(".")
+            name = parts[0]
+            cin = name.endswith("c") and name in ("madc", "addc", "subc")
+            cout = parts[-1] == "cc"
+            if name in ("mad", "madc"):
+                pr = s[0] * s[1]
+                pr = (pr & M32) if parts[1] == "lo" else (pr >> 32)
+                t = pr + s[2] + (cc if cin else 0)
+            elif name in ("add", "addc"):
+                t = s[0] + s[1] + (cc if cin else 0)
+            elif name in ("sub", "subc"):
+                t = s[0] - s[1] - (cc if cin else 0)
+            else:
+                raise ValueError(op)
+            env[dst] = t & M32
+            if cout:
+                cc = 1 if (t < 0 or t > M32) else 0
+            # (PTX leaves CC unchanged when .cc is absent)
+        return env
+
+    # ---- PTX text -------------------------------------------------------
+    def ptx(self, operand):
+        """operand: map reg name -> asm operand string ('%3') for inputs/outputs; others become .reg temps"""
+        temps = []
+        seen = set()
+        for op, dst, srcs in self.ops:
+            for r in [dst] + [x for x in srcs if not isinstance(x, int)]:
+                if r not in operand and r not in seen:
+                    seen.add(r)
+                    temps.append(r)
+        lines = ["{"]
+        for i in range(0, len(temps), 12):
+            lines.append(".reg .u32 " + ", ".join(temps[i:i + 12]) + ";")
+
+        def o(x):
+            if isinstance(x, int):
+                return str(x)
+            return operand.get(x, x)
+
+        for op, dst, srcs in self.ops:
+            if op.startswith("shf.l"):
+                lines.append("shf.l.clamp.b32 %s, %s, %s, %s;" % (o(dst), o(srcs[0]), o(srcs[1]), o(srcs[2])))
+            elif op.startswith("and"):
+                lines.append("and.b32 %s, %s, %s;" % (o(dst), o(srcs[0]), o(srcs[1])))
+            else:
+                lines.append("%s %s, %s;" % (op, o(dst), ", ".join(o(x) for x in srcs)))
+        lines.append("}")
+        return lines
+
+
+def chain_row(pr, arr, defined, ai, terms, first_free):
+    """Accumulate products ai*bj at consecutive register pairs of `arr`.
+    terms: list of (lo_index, bj_name) with lo_index increasing by 2. defined: set of indices already holding data."""
+    first = True
+    last_hi_defined = False
+    for lo, bj in terms:
+        hi = lo + 1
+        lo_def, hi_def = lo in defined, hi in defined
+        opl = ("mad.lo.cc.u32" if first else "madc.lo.cc.u32")
+        pr.emit(opl, arr % lo, ai, bj, (arr % lo) if lo_def else 0)
+        pr.emit("madc.hi.cc.u32", arr % hi, ai, bj, (arr % hi) if hi_def else 0)
+        defined.add(lo)
+        defined.add(hi)
+        last_hi_defined = hi_def
+        first = False
+        top = hi
+    # propagate the carry through every higher limb that already holds data, then into a fresh limb
+    k = top + 1
+    while k in defined:
+        pr.emit("addc.cc.u32", arr % k, arr % k, 0)
+        last_hi_defined = True
+        k += 1
+    if last_hi_defined and k < first_free:
+        pr.emit("addc.u32", arr % k, 0, 0)
+        defined.add(k)
+
+
+def gen_reduce(pr, c, out):
+    """c[0..15] (names) -> out[0..7], value = c mod p in [0, 2^256)."""
+    # even columns: (c0,c1) += 38*c8 ; (c2,c3) += 38*c10 ; ...
+    first = True
+    for j in (0, 2, 4, 6):
+        pr.emit("mad.lo.cc.u32" if first else "madc.lo.cc.u32", c[j], c[8 + j], 38, c[j])
+        pr.emit("madc.hi.cc.u32", c[j + 1], c[8 + j], 38, c[j + 1])
+        first = False
+    pr.emit("addc.u32", "t8", 0, 0)
+    # odd columns: fresh products
+    for j in (1, 3, 5, 7):
+        pr.emit("mul.lo.u32", "q%d" % j, c[8 + j], 38)
+        pr.emit("mul.hi.u32", "q%d" % (j + 1), c[8 + j], 38)
+    pr.emit("add.cc.u32", c[1], c[1], "q1")
+    for k in range(2, 8):
+        pr.emit("addc.cc.u32", c[k], c[k], "q%d" % k)
+    pr.emit("addc.u32", "t8", "t8", "q8")
+    # fold the 9th limb (< 2^7): c += 38*t8
+    pr.emit("mul.lo.u32", "t8", "t8", 38)
+    pr.emit("add.cc.u32", c[0], c[0], "t8")
+    for k in range(1, 8):
+        pr.emit("addc.cc.u32", c[k], c[k], 0)
+    pr.emit("addc.u32", "t9", 0, 0)
+    # a second wrap leaves a value < 2^13 in c, so +38 cannot carry
+    pr.emit("mul.lo.u32", "t9", "t9", 38)
+    pr.emit("add.u32", out[0], c[0], "t9")
+    for k in range(1, 8):
+        if out[k] != c[k]:
+            pr.emit("add.u32", out[k], c[k], 0)
+
+
+def gen_mul():
+    pr = Prog()
+    a = ["a%d" % i for i in range(8)]
+    b = ["b%d" % i for i in range(8)]
+    E, O = "e%d", "o%d"      # o[k] holds column k+1
+    de, do = set(), set()
+    for i in range(8):
+        te = [(i + j, b[j]) for j in range(8) if (i + j) % 2 == 0]
+        to = [(i + j - 1, b[j]) for j in range(8) if (i + j) % 2 == 1]
+        if i == 0:
+            for lo, bj in te:
+                pr.emit("mul.lo.u32", E % lo, a[0], bj); pr.emit("mul.hi.u32", E % (lo + 1), a[0], bj)
+                de |= {lo, lo + 1}
+            for lo, bj in to:
+                pr.emit("mul.lo.u32", O % lo, a[0], bj); pr.emit("mul.hi.u32", O % (lo + 1), a[0], bj)
+                do |= {lo, lo + 1}
+            continue
+        chain_row(pr, E, de, a[i], te, 16)
+        chain_row(pr, O, do, a[i], to, 15)
+    assert de == set(range(16)) and do == set(range(15)), (de, do)
+    # merge: c[k] = e[k] + o[k-1]
+    pr.emit("add.cc.u32", "e1", "e1", "o0")
+    for k in range(2, 15):
+        pr.emit("addc.cc.u32", E % k, E % k, O % (k - 1))
+    pr.emit("addc.u32", "e15", "e15", "o14")
+    gen_reduce(pr, [E % k for k in range(16)], ["r%d" % k for k in range(8)])
+    return pr
+
+
+def gen_sqr():
+    pr = Prog()
+    a = ["a%d" % i for i in range(8)]
+    E, O = "e%d", "o%d"
+    de, do = set(), set()
+    for i in range(7):
+        te = [(i + j, a[j]) for j in range(i + 1, 8) if (i + j) % 2 == 0]
+        to = [(i + j - 1, a[j]) for j in range(i + 1, 8) if (i + j) % 2 == 1]
+        for arr, dset, terms, lim in ((E, de, te, 16), (O, do, to, 15)):
+            if not terms:
+                continue
+            if terms[0][0] not in dset and all(x not in dset for t in terms for x in (t[0], t[0] + 1)):
+                for lo, bj in terms:
+                    pr.emit("mul.lo.u32", arr % lo, a[i], bj); pr.emit("mul.hi.u32", arr % (lo + 1), a[i], bj)
+                    dset |= {lo, lo + 1}
+            else:
+                chain_row(pr, arr, dset, a[i], terms, lim)
+    # off-diagonal sum S occupies columns 1..14 (< 2^511); e covers even-aligned pairs, o odd-aligned
+    lo_e, hi_e = min(de), max(de)
+    lo_o, hi_o = min(do), max(do)
+    # c[k] = e[k] + o[k-1] for k in 0..15 (missing -> 0)
+    c = []
+    first = True
+    for k in range(16):
+        ek = (E % k) if k in de else None
+        ok = (O % (k - 1)) if (k - 1) in do else None
+        name = "c%d" % k
+        if ek is None and ok is None:
+            pr.emit("add.u32", name, 0, 0) if first else pr.emit("addc.cc.u32", name, 0, 0)
+        elif first:
+            # no carry can exist yet
+            if ek is not None and ok is not None:
+                pr.emit("add.cc.u32", name, ek, ok); first = False
+            else:
+                pr.emit("add.u32", name, ek if ek is not None else ok, 0)
+        else:
+            pr.emit("addc.cc.u32", name, ek if ek is not None else 0, ok if ok is not None else 0)
+        c.append(name)
+    # double: c = 2*S
+    for k in range(15, 0, -1):
+        pr.emit("shf.l", c[k], c[k - 1], c[k], 1)
+    pr.emit("shf.l", c[0], 0, c[0], 1)
+    # add the diagonal a_i^2 at column 2i
+    for i in range(8):
+        pr.emit("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", c[2 * i], a[i], a[i], c[2 * i])
+        pr.emit("madc.hi.cc.u32", c[2 * i + 1], a[i], a[i], c[2 * i + 1])
+    gen_reduce(pr, c, ["r%d" % k for k in range(8)])
+    return pr
+
+
+def limbs(v, n=8):
+    return [(v >> (32 * i)) & M32 for i in range(n)]
+
+
+def check(pr, is_sqr):
+    rnd = random.Random(1234)
+    specials = [0, 1, 2, P - 1, P, P + 1, 2 * P, 2 * P + 1, (1 << 256) - 1, (1 << 256) - 38, (1 << 256) - 39,
+                (1 << 255), (1 << 255) - 1, M32, M32 << 224, int("f" * 8 + "0" * 8, 16) * ((1 << 256) // ((1 << 64) - 1))]
+    cases = [(x, y) for x in specials for y in specials]
+    for _ in range(3000):
+        x = rnd.getrandbits(256); y = rnd.getrandbits(256)
+        if rnd.random() < 0.3:
+            x |= ((1 << 256) - 1) ^ ((1 << rnd.randrange(256)) - 1)
+        if rnd.random() < 0.3:
+            y = ((1 << 256) - 1) >> rnd.randrange(64)
+        cases.append((x, y))
+    for x, y in cases:
+        if is_sqr:
+            y = x
+        env = {"a%d" % i: v for i, v in enumerate(limbs(x))}
+        env.update({"b%d" % i: v for i, v in enumerate(limbs(y))})
+        out = pr.run(env)
+        r = sum(out["r%d" % i] << (32 * i) for i in range(8))
+        assert r < (1 << 256)
+        assert r % P == (x * y) % P, (hex(x), hex(y), hex(r))
+
+
+def emit_function(name, pr, nin):
+    operand = {}
+    idx = 0
+    for k in range(8):
+        operand["r%d" % k] = "%%%d" % idx; idx += 1
+    for k in range(8):
+        operand["a%d" % k] = "%%%d" % idx; idx += 1
+    if nin == 2:
+        for k in range(8):
+            operand["b%d" % k] = "%%%d" % idx; idx += 1
+    lines = pr.ptx(operand)
+    body = "\n".join('      "%s\\n\\t"' % ln for ln in lines)
+    outs = ", ".join('"=&r"(r[%d])' % k for k in range(8))
+    ins = ", ".join('"r"(a[%d])' % k for k in range(8))
+    if nin == 2:
+        ins += ", " + ", ".join('"r"(b[%d])' % k for k in range(8))
+        sig = "uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]"
+    else:
+        sig = "uint32_t (&r)[8], const uint32_t (&a)[8]"
+    return ("__device__ __forceinline__ void %s(%s) {\n  asm(\n%s\n      : %s\n      : %s);\n}\n" % (name, sig, body, outs, ins))
+
+
+def count(pr):
+    w = sum(1 for op, _, _ in pr.ops if ".hi" in op)          # each lo/hi pair fuses into one IMAD.WIDE
+    other = sum(1 for op, _, _ in pr.ops if not op.startswith(("mul", "mad")))
+    return w, other
+
+
+if __name__ == "__main__":
+    m, s = gen_mul(), gen_sqr()
+    check(m, False)
+    check(s, True)
+    hdr = ("// GENERATED by tools/gen_fe_asm.py — do not edit.\n"
+           "// GF(2^255-19) multiply / square on 8 saturated 32-bit limbs; mad.lo.cc/madc.hi.cc pairs fuse to IMAD.WIDE.U32.X.\n"
+           "// Every sequence below was simulated against Python big integers by the generator before being emitted.\n"
+           "#pragma once\n#include <cstdint>\n\n")
+    txt = hdr + emit_function("fe_mul_asm", m, 2) + "\n" + emit_function("fe_sqr_asm", s, 1)
+    path = os.path.join(ROOT, "hotstuff_b200", "csrc", "fe_asm.cuh")
+    open(path, "w").write(txt)
+    print("mul: %d wide-mads + %d other ops; sqr: %d wide-mads + %d other ops -> %s" % (count(m) + count(s) + (path,)))
