@@ -26,6 +26,8 @@ SIGNATURES = {
     "hs_verify_var_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),
     "hs_verify_committee_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),
     "hs_digest32_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_verify_msgs": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_u32, c_void_p]),
+    "hs_verify_msgs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_u32, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -1,22 +1,55 @@
 // hs_engine.cu — sm_100a kernels + the C ABI of include/hs_crypto.h.
 //
 // Hot path of asonnino/hotstuff's crypto crate (crypto/src/lib.rs:200-219 + the SHA-512 Digest call sites) rebuilt for
-// B200: one thread verifies one signature end to end (SHA-512 -> mod l -> decompress -> double-scalar mult -> compare),
-// a warp ballots 32 verdicts into one bitmap word.  No CPU path: if CUDA fails the call returns an error.
+// B200.  No CPU path: if CUDA fails the call returns an error and the caller must reject.
+//
+// Pipeline of one verify call (all on one stream):
+//   k_key_lookup      pk bytes -> committee index through a device hash table (skipped when the caller gives indices)
+//   k_verify_main<C>  committee keys: SHA-512(R||A||M) -> k mod l -> [k](-A) + [S]B by table gathers only
+//                     (22 + 16 mixed additions, no doublings, no decompression) -> projective (X:Y:Z) + meta
+//   k_verify_main<G>  records whose key is not registered (compacted list): decompress A, radix-16 window for [k](-A)
+//   k_verify_finish   Montgomery-batched inversion of 16 Z's per thread, affine compare with R's encoding,
+//                     small-order rule, 32 verdicts -> one bitmap word
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/hs_crypto.h"
 #include "verify_core.cuh"
 
 #define HS_THREADS 128
+#define HS_FINISH_GROUP 16  // signatures whose Z's share one inversion
+#define HS_NO_KEY 0xffffffffu
 
-// ------------------------------------------------------------------------------------------------ record staging
+// ------------------------------------------------------------------------------------------------ input layout
+// One descriptor covers every caller-facing layout: packed hs_rec128 records, separate sig/pk arrays with
+// variable-length messages, QC votes sharing one digest, committee-indexed votes.
+struct in_layout {
+  const uint8_t *sig;   // 64-byte signature of record i at sig + i * sig_stride
+  size_t sig_stride;
+  const uint8_t *pk;    // 32-byte key of record i at pk + i * pk_stride (nullptr when only indices are given)
+  size_t pk_stride;
+  const uint32_t *vidx; // committee index per record (caller-given or produced by k_key_lookup); nullptr = none
+  const uint8_t *msg;   // message i: off ? msg + off[i] : msg + (midx ? midx[i] : i) * msg_stride
+  size_t msg_stride;
+  const uint32_t *midx;
+  const uint64_t *off;
+  uint64_t fixed_len;   // message length when off == nullptr
+  int aos128;           // 1: sig/pk/msg are the fields of packed 128-byte records at `sig` (coalesced staged loads)
+};
+
+__device__ __forceinline__ void load32(uint32_t (&w)[8], const uint8_t *p) {
+  const uint32_t *s = reinterpret_cast<const uint32_t *>(p);  // every 32-byte field is 4-byte aligned in all layouts
+#pragma unroll
+  for (int i = 0; i < 8; i++) w[i] = __ldg(s + i);
+}
+
 // A warp loads its 32 packed 128-byte records (4 KB) with fully coalesced 16-byte accesses, parks them in shared
 // memory under an XOR swizzle, and every lane then reads back its own record conflict-free.
 __device__ __forceinline__ void warp_load_rec128(uint32_t (&sig_r)[8], uint32_t (&sig_s)[8], uint32_t (&pk)[8], uint32_t (&msg)[8],
@@ -42,111 +75,221 @@ __device__ __forceinline__ void warp_load_rec128(uint32_t (&sig_r)[8], uint32_t 
   msg[0] = q[6].x; msg[1] = q[6].y; msg[2] = q[6].z; msg[3] = q[6].w; msg[4] = q[7].x; msg[5] = q[7].y; msg[6] = q[7].z; msg[7] = q[7].w;
 }
 
-__device__ __forceinline__ void load32(uint32_t (&w)[8], const uint8_t *p) {
-  // 32-byte field at a 4-byte-aligned address (sig/pk arrays of the var / vote / committee layouts)
-  const uint32_t *s = reinterpret_cast<const uint32_t *>(p);
-#pragma unroll
-  for (int i = 0; i < 8; i++) w[i] = __ldg(s + i);
-}
-
-__device__ __forceinline__ void emit_verdict(uint32_t fl, uint32_t mode, bool active, size_t idx, uint32_t *bitmap, uint8_t *flags_out) {
-  uint32_t bit = active && ((mode == HS_MODE_STRICT) ? (fl & HS_F_STRICT) : (fl & HS_F_EQ));
-  uint32_t word = __ballot_sync(0xffffffffu, bit);
-  if ((threadIdx.x & 31) == 0 && active) bitmap[idx >> 5] = word;
-  if (flags_out && active) flags_out[idx] = (uint8_t)fl;
-}
-
-// ------------------------------------------------------------------------------------------------ generic-key kernels
-// packed records {sig, pk, msg32}: Signature::verify over n independent triples
-__global__ void __launch_bounds__(HS_THREADS) k_verify_rec128(const uint4 *__restrict__ recs, size_t n, const ge_niels *__restrict__ btable,
-                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out) {
-  __shared__ uint4 stage[HS_THREADS / 32][256];
-  const size_t idx = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
-  const size_t warp_first = idx & ~(size_t)31;
-  if (warp_first >= n) return;
-  const bool active = idx < n;
-  uint32_t R[8], S[8], A[8], M[8], h[16];
-  warp_load_rec128(R, S, A, M, recs, n, warp_first, stage[threadIdx.x >> 5]);
-  sha512_ram32(h, R, A, M);
-  ge_cached tab[9];
-  uint32_t fl = verify_generic_core(R, S, A, h, btable, tab);
-  emit_verdict(fl, mode, active, idx, bitmap, flags_out);
-}
-
-// variable-length messages; also serves the shared-message vote layout through strides
-struct var_layout {
-  const uint8_t *sig;
-  const uint8_t *pk;
-  const uint8_t *msgs;
-  const uint64_t *off;  // nullptr -> every item uses msgs[0 .. fixed_len)
-  size_t sig_stride, pk_stride;
-  uint64_t fixed_len;
+// ------------------------------------------------------------------------------------------------ committee key lookup
+// Open-addressing hash table over the registered keys: slot -> key index (HS_NO_KEY = empty).  Built on the host at
+// registration (hashing only), probed here by one thread per record.
+struct key_table {
+  const uint32_t *slots;
+  uint32_t mask;  // capacity - 1 (power of two)
+  const uint8_t *pks;
+  uint32_t n_keys;
 };
-__global__ void __launch_bounds__(HS_THREADS) k_verify_var(var_layout L, size_t n, const ge_niels *__restrict__ btable, uint32_t mode,
-                                                            uint32_t *__restrict__ bitmap, uint8_t *flags_out) {
-  const size_t idx = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
-  const size_t warp_first = idx & ~(size_t)31;
-  if (warp_first >= n) return;
-  const bool active = idx < n;
-  const size_t i = active ? idx : n - 1;
-  uint32_t R[8], S[8], A[8], h[16];
-  load32(R, L.sig + i * L.sig_stride);
-  load32(S, L.sig + i * L.sig_stride + 32);
-  load32(A, L.pk + i * L.pk_stride);
-  const uint8_t *m = L.off ? L.msgs + L.off[i] : L.msgs;
-  uint64_t len = L.off ? (L.off[i + 1] - L.off[i]) : L.fixed_len;
-  uint64_t pre[8];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    pre[j] = be64_from_le32(R[2 * j], R[2 * j + 1]);
-    pre[4 + j] = be64_from_le32(A[2 * j], A[2 * j + 1]);
+__host__ __device__ inline uint32_t key_hash(const uint32_t *w) {
+  uint32_t h = 0x9e3779b9u;
+  for (int i = 0; i < 8; i++) {
+    h ^= w[i];
+    h *= 0x85ebca6bu;
+    h ^= h >> 15;
   }
-  sha512_prefix_msg(h, pre, 8, m, len);
-  ge_cached tab[9];
-  uint32_t fl = verify_generic_core(R, S, A, h, btable, tab);
-  emit_verdict(fl, mode, active, idx, bitmap, flags_out);
+  return h;
+}
+__global__ void __launch_bounds__(256) k_key_lookup(in_layout L, size_t n, key_table T, uint32_t *__restrict__ out_vidx) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8];
+  load32(k, L.pk + i * L.pk_stride);
+  uint32_t found = HS_NO_KEY;
+  uint32_t h = key_hash(k) & T.mask;
+  for (uint32_t probe = 0; probe <= T.mask; probe++) {
+    uint32_t idx = __ldg(T.slots + h);
+    if (idx == HS_NO_KEY) break;
+    const uint32_t *cand = reinterpret_cast<const uint32_t *>(T.pks + (size_t)idx * 32);
+    uint32_t diff = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) diff |= __ldg(cand + j) ^ k[j];
+    if (diff == 0) {
+      found = idx;
+      break;
+    }
+    h = (h + 1) & T.mask;
+  }
+  out_vidx[i] = found;
 }
 
-// ------------------------------------------------------------------------------------------------ committee kernel
-__global__ void __launch_bounds__(HS_THREADS) k_verify_committee(const uint32_t *__restrict__ vidx, const uint8_t *__restrict__ sig,
-                                                                  const uint32_t *__restrict__ midx, const uint8_t *__restrict__ digests, size_t n,
-                                                                  const uint8_t *__restrict__ pks, const uint8_t *__restrict__ key_flags, uint32_t n_keys,
-                                                                  const ge_niels *__restrict__ btable, const ge_niels *__restrict__ atables, uint32_t mode,
-                                                                  uint32_t *__restrict__ bitmap, uint8_t *flags_out) {
-  const size_t idx = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
-  const size_t warp_first = idx & ~(size_t)31;
-  if (warp_first >= n) return;
-  const bool active = idx < n;
-  const size_t i = active ? idx : n - 1;
-  uint32_t v = __ldg(vidx + i);
-  const bool known = v < n_keys;  // unknown authority: reject (messages.rs:57-61 rejects it before crypto)
-  if (!known) v = 0;
-  uint32_t R[8], S[8], A[8], M[8], h[16];
-  load32(R, sig + i * 64);
-  load32(S, sig + i * 64 + 32);
-  load32(A, pks + (size_t)v * 32);
-  load32(M, digests + (size_t)(midx ? __ldg(midx + i) : 0u) * 32);
-  sha512_ram32(h, R, A, M);
-  uint32_t fl = verify_committee_core(R, S, h, btable, atables + (size_t)v * HS_COMB_TABLE_NIELS, known ? key_flags[v] : 0u);
-  emit_verdict(fl, mode, active, idx, bitmap, flags_out);
+// ------------------------------------------------------------------------------------------------ phase 1: main
+struct main_out {
+  fe *xyz;         // 3 field elements per record: X, Y, Z of R' = [S]B + [k](-A)
+  uint8_t *meta;   // HS_META_* per record
+  uint32_t *miss_list;
+  uint32_t *miss_count;
+};
+struct committee_tables {
+  const uint8_t *pks;
+  const uint8_t *key_flags;
+  uint32_t n_keys;
+  const ge_niels *atables;
+};
+
+// Grid-stride over records so the same kernel serves a full launch (one pass) and the compacted miss list, whose length
+// only the device knows (n_ptr): no host round trip between the committee pass and the generic pass.
+template <bool COMMITTEE>
+__global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
+                                                             const uint32_t *__restrict__ index_list, const ge_niels *__restrict__ btable,
+                                                             committee_tables C, main_out O) {
+  __shared__ uint4 stage[HS_THREADS / 32][256];
+  const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
+  for (size_t base = (size_t)blockIdx.x * HS_THREADS; base < n; base += (size_t)gridDim.x * HS_THREADS) {
+  const size_t t = base + threadIdx.x;
+  const size_t warp_first = t & ~(size_t)31;
+  if (warp_first >= n) continue;
+  const bool active = t < n;
+  size_t i = active ? t : n - 1;
+  uint32_t R[8], S[8], A[8], h[16];
+  uint32_t v = 0;
+  bool have_key = true;
+  if (L.aos128 && !index_list) {
+    uint32_t M[8];
+    warp_load_rec128(R, S, A, M, reinterpret_cast<const uint4 *>(L.sig), n, warp_first, stage[threadIdx.x >> 5]);
+    if (COMMITTEE) {
+      v = __ldg(L.vidx + i);
+      have_key = v < C.n_keys;
+      if (!have_key) v = 0;
+      load32(A, C.pks + (size_t)v * 32);  // hash the registered key bytes (identical to the record's on a lookup hit)
+    }
+    sha512_ram32(h, R, A, M);
+  } else {
+    if (index_list) i = index_list[i];
+    load32(R, L.sig + i * L.sig_stride);
+    load32(S, L.sig + i * L.sig_stride + 32);
+    if (COMMITTEE) {
+      v = __ldg(L.vidx + i);
+      have_key = v < C.n_keys;
+      if (!have_key) v = 0;
+      load32(A, C.pks + (size_t)v * 32);
+    } else {
+      load32(A, L.pk + i * L.pk_stride);
+    }
+    const uint8_t *m = L.off ? L.msg + L.off[i] : L.msg + (size_t)(L.midx ? __ldg(L.midx + i) : i) * L.msg_stride;
+    const uint64_t len = L.off ? (L.off[i + 1] - L.off[i]) : L.fixed_len;
+    if (len == 32 && ((reinterpret_cast<uintptr_t>(m) & 3u) == 0)) {
+      uint32_t M[8];
+      load32(M, m);
+      sha512_ram32(h, R, A, M);
+    } else {
+      uint64_t pre[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        pre[j] = be64_from_le32(R[2 * j], R[2 * j + 1]);
+        pre[4 + j] = be64_from_le32(A[2 * j], A[2 * j + 1]);
+      }
+      sha512_prefix_msg(h, pre, 8, m, len);
+    }
+  }
+  ge_ext acc;
+  uint32_t meta;
+  if (COMMITTEE) {
+    meta = verify_committee_main(acc, R, S, h, btable, C.atables + (size_t)v * HS_A_TABLE_NIELS, have_key ? C.key_flags[v] : 0u);
+    if (!have_key) {
+      meta = HS_META_MISS;
+      if (active && O.miss_list) O.miss_list[atomicAdd(O.miss_count, 1u)] = (uint32_t)i;
+    }
+  } else {
+    ge_cached tab[9];
+    meta = verify_generic_main(acc, R, S, A, h, btable, tab);
+  }
+  if (!active) continue;
+  if (!(meta & HS_META_PARSE_OK)) {  // keep the batched inversion well-defined for rejected records
+    fe_set0(acc.X);
+    fe_set1(acc.Y);
+    fe_set1(acc.Z);
+  }
+  uint4 *dst = reinterpret_cast<uint4 *>(O.xyz + i * 3);
+  dst[0] = make_uint4(acc.X.v[0], acc.X.v[1], acc.X.v[2], acc.X.v[3]);
+  dst[1] = make_uint4(acc.X.v[4], acc.X.v[5], acc.X.v[6], acc.X.v[7]);
+  dst[2] = make_uint4(acc.Y.v[0], acc.Y.v[1], acc.Y.v[2], acc.Y.v[3]);
+  dst[3] = make_uint4(acc.Y.v[4], acc.Y.v[5], acc.Y.v[6], acc.Y.v[7]);
+  dst[4] = make_uint4(acc.Z.v[0], acc.Z.v[1], acc.Z.v[2], acc.Z.v[3]);
+  dst[5] = make_uint4(acc.Z.v[4], acc.Z.v[5], acc.Z.v[6], acc.Z.v[7]);
+  O.meta[i] = (uint8_t)meta;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ phase 2: finish
+__device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(p);
+  uint4 a = s[0], b = s[1];
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+}
+// One thread owns HS_FINISH_GROUP consecutive records: prefix products of their Z's, ONE inversion, back-substitution,
+// affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into one bitmap word.
+__global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_t n, const fe *__restrict__ xyz, const uint8_t *__restrict__ meta,
+                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out) {
+  const size_t t = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
+  const size_t first = t * HS_FINISH_GROUP;
+  uint32_t bits = 0;
+  if (first < n) {
+    const int cnt = (int)((n - first < HS_FINISH_GROUP) ? (n - first) : HS_FINISH_GROUP);
+    fe prod[HS_FINISH_GROUP];
+    fe run;
+    fe_set1(run);
+#pragma unroll 1
+    for (int c = 0; c < cnt; c++) {
+      fe Z;
+      fe_load_global(Z, xyz + (first + c) * 3 + 2);
+      if (fe_is_zero(Z)) fe_set1(Z);  // cannot happen for curve points; keeps one bad record from poisoning the group
+      fe_mul(run, run, Z);
+      prod[c] = run;
+    }
+    fe u;
+    fe_invert(u, run);
+#pragma unroll 1
+    for (int c = cnt - 1; c >= 0; c--) {
+      const size_t i = first + c;
+      fe X, Y, Z, zinv;
+      fe_load_global(X, xyz + i * 3 + 0);
+      fe_load_global(Y, xyz + i * 3 + 1);
+      fe_load_global(Z, xyz + i * 3 + 2);
+      const uint32_t zero_z = fe_is_zero(Z);
+      if (zero_z) fe_set1(Z);
+      if (c > 0) fe_mul(zinv, u, prod[c - 1]);
+      else zinv = u;
+      fe_mul(u, u, Z);
+      uint32_t R[8];
+      load32(R, L.sig + i * L.sig_stride);
+      uint32_t m = meta[i];
+      if (zero_z) m &= ~HS_META_PARSE_OK;
+      const uint32_t fl = verify_flags_from(X, Y, zinv, R, m);
+      if (flags_out) flags_out[i] = (uint8_t)fl;
+      const uint32_t ok = (mode == HS_MODE_STRICT) ? (fl & HS_F_STRICT) : (fl & HS_F_EQ);
+      if (ok) bits |= 1u << c;
+    }
+  }
+  // lanes 2j and 2j+1 hold bits [32j .. 32j+15] and [32j+16 .. 32j+31] of word (t/2)
+  const uint32_t other = __shfl_xor_sync(0xffffffffu, bits, 1);
+  if ((threadIdx.x & 1) == 0 && first < n) bitmap[t >> 1] = bits | (other << 16);
 }
 
 // ------------------------------------------------------------------------------------------------ table construction
-// thread (point p, window w): decompress point p (or take B when encs == nullptr), optionally negate, fill one window
-__global__ void __launch_bounds__(HS_THREADS) k_build_comb(const uint8_t *__restrict__ encs, size_t n_points, int negate, ge_niels *tables,
-                                                            uint8_t *key_flags) {
+// thread = (point p, window w, block b of HS_BUILD_BLOCK entries)
+#define HS_BUILD_BLOCK 64
+__global__ void __launch_bounds__(HS_THREADS) k_build_comb(const uint8_t *__restrict__ encs, size_t n_points, int negate, int W, int n_windows,
+                                                            ge_niels *tables, uint8_t *key_flags) {
+  const int entries = 1 << (W - 1);
+  const int blocks_per_window = entries / HS_BUILD_BLOCK;
   const size_t t = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
-  const size_t p = t / HS_COMB_WINDOWS;
-  const int w = (int)(t % HS_COMB_WINDOWS);
+  const size_t per_point = (size_t)n_windows * blocks_per_window;
+  const size_t p = t / per_point;
   if (p >= n_points) return;
+  const int w = (int)((t % per_point) / blocks_per_window);
+  const int b = (int)(t % blocks_per_window);
   ge_ext P;
   if (encs) {
     uint32_t e[8];
     load32(e, encs + p * 32);
     uint32_t ok = ge_decompress(P, e);
     uint32_t small = ge_enc_is_small_order(e);
-    if (w == 0 && key_flags) key_flags[p] = (uint8_t)((ok & 1u) | (small << 1));
-    if (!ok) ge_identity(P);  // table of a rejected key is never used for an accept (flag bit0 = 0)
+    if (w == 0 && b == 0 && key_flags) key_flags[p] = (uint8_t)((ok & 1u) | (small << 1));
+    if (!ok) ge_identity(P);  // the table of a rejected key is never used for an accept (flag bit0 = 0)
   } else {
     ge_basepoint(P);
   }
@@ -155,39 +298,47 @@ __global__ void __launch_bounds__(HS_THREADS) k_build_comb(const uint8_t *__rest
     ge_neg(Q, P);
     P = Q;
   }
-  comb_build_window(tables + p * HS_COMB_TABLE_NIELS, P, w);
+  fe prod[HS_BUILD_BLOCK];
+  comb_build_block(tables + p * ((size_t)n_windows << (W - 1)), P, W, w, b * HS_BUILD_BLOCK, HS_BUILD_BLOCK, prod);
 }
 
-// ------------------------------------------------------------------------------------------------ Digest kernel
-__global__ void __launch_bounds__(HS_THREADS) k_digest32(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off, size_t n,
-                                                          uint32_t *__restrict__ out) {
+// ------------------------------------------------------------------------------------------------ Digest kernels
+__global__ void __launch_bounds__(HS_THREADS) k_digest32(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off, uint64_t fixed_len,
+                                                          size_t n, uint32_t *__restrict__ out) {
   const size_t i = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
   if (i >= n) return;
   uint32_t h[16];
   uint64_t pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  sha512_prefix_msg(h, pre, 0, data + off[i], off[i + 1] - off[i]);
-#pragma unroll
-  for (int j = 0; j < 8; j++) out[i * 8 + j] = h[j];
+  const uint8_t *m = off ? data + off[i] : data + i * fixed_len;
+  const uint64_t len = off ? off[i + 1] - off[i] : fixed_len;
+  sha512_prefix_msg(h, pre, 0, m, len);
+  uint4 *dst = reinterpret_cast<uint4 *>(out + i * 8);
+  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
 // ================================================================================================ host side
+struct dev_buf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
 struct hs_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   ge_niels *d_btable = nullptr;
   // committee
   size_t n_keys = 0;
   uint8_t *d_pks = nullptr;
   uint8_t *d_key_flags = nullptr;
   ge_niels *d_atables = nullptr;
-  // grow-only device scratch for the host-pointer entry points
-  void *d_in = nullptr;
-  size_t d_in_cap = 0;
-  void *d_in2 = nullptr;
-  size_t d_in2_cap = 0;
-  void *d_out = nullptr;
-  size_t d_out_cap = 0;
-  uint64_t launches = 0;
+  uint32_t *d_slots = nullptr;
+  uint32_t slot_mask = 0;
+  // grow-only device scratch
+  dev_buf in[2], digest[2], xyz, meta, vidx, miss, out;
+  uint32_t *d_miss_count = nullptr;
+  uint32_t *h_miss_count = nullptr;  // pinned
+  std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::string err = "ok";
 };
@@ -202,24 +353,90 @@ static int fail(hs_ctx *c, int code, const char *what, cudaError_t e = cudaSucce
   }
   return code;
 }
-#define HS_CUDA(c, call)                                          \
-  do {                                                            \
-    cudaError_t e__ = (call);                                     \
+#define HS_CUDA(c, call)                                               \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
     if (e__ != cudaSuccess) return fail((c), HS_ERR_CUDA, #call, e__); \
   } while (0)
+#define HS_TRY(expr)          \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__) return rc__;    \
+  } while (0)
 
-static int ensure(hs_ctx *c, void **p, size_t *cap, size_t need) {
-  if (need <= *cap) return HS_OK;
-  if (*p) cudaFree(*p);
-  *p = nullptr;
-  *cap = 0;
+static int ensure(hs_ctx *c, dev_buf &b, size_t need) {
+  if (need <= b.cap) return HS_OK;
+  if (b.p) {
+    cudaDeviceSynchronize();  // the old block may still be in flight on another stream
+    cudaFree(b.p);
+  }
+  b.p = nullptr;
+  b.cap = 0;
   size_t want = need + need / 4 + 4096;
-  cudaError_t e = cudaMalloc(p, want);
+  cudaError_t e = cudaMalloc(&b.p, want);
   if (e != cudaSuccess) return fail(c, HS_ERR_NOMEM, "cudaMalloc scratch", e);
-  *cap = want;
+  b.cap = want;
   return HS_OK;
 }
-static inline unsigned blocks_for(size_t n) { return (unsigned)((n + HS_THREADS - 1) / HS_THREADS); }
+static inline unsigned blocks_for(size_t n, unsigned per = HS_THREADS) { return (unsigned)((n + per - 1) / per); }
+
+static int launch_build(hs_ctx *c, const uint8_t *d_encs, size_t n_points, int negate, int W, int n_windows, ge_niels *tables, uint8_t *flags) {
+  size_t threads = n_points * (size_t)n_windows * ((1u << (W - 1)) / HS_BUILD_BLOCK);
+  k_build_comb<<<blocks_for(threads), HS_THREADS, 0, c->stream>>>(d_encs, n_points, negate, W, n_windows, tables, flags);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+
+// Runs lookup (optional) -> main (committee and/or generic) -> finish on `stream` for a device-resident layout.
+// use_lookup: L.pk is valid and a committee is registered -> resolve indices on the device.
+static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed) {
+  if (n == 0) return HS_OK;
+  HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, c->meta, n));
+  main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, nullptr, nullptr};
+  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables};
+  const bool committee = c->n_keys > 0 && (indexed || L.pk);
+  if (indexed && c->n_keys == 0) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
+  if (committee) {
+    if (!indexed) {
+      HS_TRY(ensure(c, c->vidx, n * 4));
+      HS_TRY(ensure(c, c->miss, n * 4));
+      key_table T{c->d_slots, c->slot_mask, c->d_pks, (uint32_t)c->n_keys};
+      k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)c->vidx.p);
+      c->launches++;
+      L.vidx = (const uint32_t *)c->vidx.p;
+      O.miss_list = (uint32_t *)c->miss.p;
+      O.miss_count = c->d_miss_count;
+      HS_CUDA(c, cudaMemsetAsync(c->d_miss_count, 0, 4, stream));
+    }
+    k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+    if (!indexed) {
+      // records whose key is not registered: generic path over the compacted list; the count stays on the device
+      unsigned grid = blocks_for(n);
+      if (grid > 148u * 4u) grid = 148u * 4u;
+      k_verify_main<false><<<grid, HS_THREADS, 0, stream>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O);
+      c->launches++;
+      HS_CUDA(c, cudaGetLastError());
+    }
+  } else {
+    k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+  }
+  const size_t fin_threads = (n + HS_FINISH_GROUP - 1) / HS_FINISH_GROUP;
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, nullptr);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+
+static in_layout layout_rec128(const void *d_recs) {
+  const uint8_t *r = (const uint8_t *)d_recs;
+  return in_layout{r, 128, r + 64, 128, nullptr, r + 96, 128, nullptr, nullptr, 32, 1};
+}
 
 extern "C" {
 
@@ -232,11 +449,16 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   c->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * HS_COMB_TABLE_NIELS);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+    e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * HS_B_TABLE_NIELS);
   if (e == cudaSuccess) {
-    k_build_comb<<<blocks_for(HS_COMB_WINDOWS), HS_THREADS, 0, c->stream>>>(nullptr, 1, 0, c->d_btable, nullptr);
-    c->launches++;
-    e = cudaGetLastError();
+    if (launch_build(c, nullptr, 1, 0, HS_B_W, HS_B_WINDOWS, c->d_btable, nullptr) != HS_OK) e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
@@ -251,20 +473,26 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
 void hs_ctx_destroy(hs_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaDeviceSynchronize();
   cudaFree(c->d_btable);
   cudaFree(c->d_pks);
   cudaFree(c->d_key_flags);
   cudaFree(c->d_atables);
-  cudaFree(c->d_in);
-  cudaFree(c->d_in2);
-  cudaFree(c->d_out);
+  cudaFree(c->d_slots);
+  cudaFree(c->d_miss_count);
+  if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
+  for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->xyz, &c->meta, &c->vidx, &c->miss, &c->out}) cudaFree(b->p);
+  for (int i = 0; i < 2; i++) {
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
 }
 
 const char *hs_last_error(const hs_ctx *c) { return c ? c->err.c_str() : "null context"; }
-uint64_t hs_kernel_launches(const hs_ctx *c) { return c ? c->launches : 0; }
+uint64_t hs_kernel_launches(const hs_ctx *c) { return c ? c->launches.load() : 0; }
 
 void *hs_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -275,55 +503,109 @@ void hs_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
-// ---- device-resident entry points
-int hs_verify_rec128_dev(hs_ctx *c, const void *d_recs, size_t n, uint32_t mode, void *d_bitmap, void *stream) {
-  if (!c || (!d_recs && n) || (!d_bitmap && n) || mode > 1) return fail(c, HS_ERR_ARG, "hs_verify_rec128_dev: bad argument");
-  if (n == 0) return HS_OK;
+// ---- committee registration
+int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out_valid_bitmap) {
+  if (!c || (N && !pks) || N >= HS_NO_KEY) return fail(c, HS_ERR_ARG, "hs_committee_register: bad argument");
+  std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
-  k_verify_rec128<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint4 *)d_recs, n, c->d_btable, mode, (uint32_t *)d_bitmap, nullptr);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
+  HS_CUDA(c, cudaDeviceSynchronize());
+  cudaFree(c->d_pks);
+  cudaFree(c->d_key_flags);
+  cudaFree(c->d_atables);
+  cudaFree(c->d_slots);
+  c->d_pks = nullptr;
+  c->d_key_flags = nullptr;
+  c->d_atables = nullptr;
+  c->d_slots = nullptr;
+  c->n_keys = 0;
+  if (N == 0) return HS_OK;
+  // host-side hash table (hashing only; first occurrence of a duplicated key wins)
+  uint32_t cap = 16;
+  while (cap < 2 * N) cap <<= 1;
+  std::vector<uint32_t> slots(cap, HS_NO_KEY);
+  for (size_t i = 0; i < N; i++) {
+    uint32_t w[8];
+    memcpy(w, pks + 32 * i, 32);
+    uint32_t h = key_hash(w) & (cap - 1);
+    bool dup = false;
+    while (slots[h] != HS_NO_KEY) {
+      if (memcmp(pks + 32 * (size_t)slots[h], pks + 32 * i, 32) == 0) {
+        dup = true;
+        break;
+      }
+      h = (h + 1) & (cap - 1);
+    }
+    if (!dup) slots[h] = (uint32_t)i;
+  }
+  HS_CUDA(c, cudaMalloc(&c->d_pks, N * 32));
+  HS_CUDA(c, cudaMalloc(&c->d_key_flags, N));
+  HS_CUDA(c, cudaMalloc(&c->d_slots, (size_t)cap * 4));
+  cudaError_t e = cudaMalloc(&c->d_atables, N * sizeof(ge_niels) * HS_A_TABLE_NIELS);
+  if (e != cudaSuccess) return fail(c, HS_ERR_NOMEM, "committee tables do not fit in device memory", e);
+  HS_CUDA(c, cudaMemcpyAsync(c->d_pks, pks, N * 32, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(c->d_slots, slots.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_TRY(launch_build(c, c->d_pks, N, 1, HS_A_W, HS_A_WINDOWS, c->d_atables, c->d_key_flags));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->slot_mask = cap - 1;
+  c->n_keys = N;
+  if (out_valid_bitmap) {
+    std::vector<uint8_t> fl(N);
+    HS_CUDA(c, cudaMemcpy(fl.data(), c->d_key_flags, N, cudaMemcpyDeviceToHost));
+    for (size_t w = 0; w < (N + 31) / 32; w++) out_valid_bitmap[w] = 0;
+    for (size_t i = 0; i < N; i++)
+      if (fl[i] & 1) out_valid_bitmap[i >> 5] |= 1u << (i & 31);
+  }
   return HS_OK;
+}
+
+// ---- device-resident entry points (one stream at a time per context: they share the context's scratch)
+int hs_verify_rec128_dev(hs_ctx *c, const void *d_recs, size_t n, uint32_t mode, void *d_bitmap, void *stream) {
+  if (!c || (n && (!d_recs || !d_bitmap)) || mode > 1) return fail(c, HS_ERR_ARG, "hs_verify_rec128_dev: bad argument");
+  HS_CUDA(c, cudaSetDevice(c->device));
+  return run_verify(c, layout_rec128(d_recs), n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, false);
 }
 int hs_verify_var_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const void *d_msgs, const void *d_off, size_t n, uint32_t mode,
                       void *d_bitmap, void *stream) {
   if (!c || mode > 1 || (n && (!d_sig || !d_pk || !d_off || !d_bitmap))) return fail(c, HS_ERR_ARG, "hs_verify_var_dev: bad argument");
-  if (n == 0) return HS_OK;
   HS_CUDA(c, cudaSetDevice(c->device));
-  var_layout L{(const uint8_t *)d_sig, (const uint8_t *)d_pk, (const uint8_t *)d_msgs, (const uint64_t *)d_off, 64, 32, 0};
-  k_verify_var<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>(L, n, c->d_btable, mode, (uint32_t *)d_bitmap, nullptr);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
-  return HS_OK;
+  in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, nullptr, (const uint8_t *)d_msgs, 0, nullptr, (const uint64_t *)d_off, 0, 0};
+  return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, false);
 }
 int hs_verify_committee_dev(hs_ctx *c, const void *d_vidx, const void *d_sig, const void *d_midx, const void *d_digests, size_t n,
                             uint32_t mode, void *d_bitmap, void *stream) {
   if (!c || mode > 1 || (n && (!d_vidx || !d_sig || !d_digests || !d_bitmap))) return fail(c, HS_ERR_ARG, "hs_verify_committee_dev: bad argument");
-  if (n == 0) return HS_OK;
-  if (c->n_keys == 0) return fail(c, HS_ERR_ARG, "hs_verify_committee: no committee registered");
   HS_CUDA(c, cudaSetDevice(c->device));
-  k_verify_committee<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint32_t *)d_vidx, (const uint8_t *)d_sig, (const uint32_t *)d_midx,
-                                                                               (const uint8_t *)d_digests, n, c->d_pks, c->d_key_flags,
-                                                                               (uint32_t)c->n_keys, c->d_btable, c->d_atables, mode,
-                                                                               (uint32_t *)d_bitmap, nullptr);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
-  return HS_OK;
+  // d_midx == NULL: every vote is over digests[0]
+  in_layout L{(const uint8_t *)d_sig, 64, nullptr, 0, (const uint32_t *)d_vidx, (const uint8_t *)d_digests, d_midx ? (size_t)32 : (size_t)0,
+              (const uint32_t *)d_midx, nullptr, 32, 0};
+  return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, true);
 }
 int hs_digest32_dev(hs_ctx *c, const void *d_data, const void *d_off, size_t n, void *d_out, void *stream) {
   if (!c || (n && (!d_off || !d_out))) return fail(c, HS_ERR_ARG, "hs_digest32_dev: bad argument");
   if (n == 0) return HS_OK;
   HS_CUDA(c, cudaSetDevice(c->device));
-  k_digest32<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_data, (const uint64_t *)d_off, n, (uint32_t *)d_out);
+  k_digest32<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_data, (const uint64_t *)d_off, 0, n, (uint32_t *)d_out);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;
+}
+int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const void *d_vidx, const void *d_msgs, size_t msg_len, size_t n,
+                       uint32_t mode, void *d_digests, void *d_bitmap, void *stream) {
+  if (!c || mode > 1 || (n && (!d_sig || (!d_pk && !d_vidx) || !d_msgs || !d_digests || !d_bitmap)))
+    return fail(c, HS_ERR_ARG, "hs_verify_msgs_dev: bad argument");
+  if (n == 0) return HS_OK;
+  HS_CUDA(c, cudaSetDevice(c->device));
+  k_digest32<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_msgs, nullptr, msg_len, n, (uint32_t *)d_digests);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, (const uint32_t *)d_vidx, (const uint8_t *)d_digests, 32, nullptr, nullptr, 32, 0};
+  return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, d_vidx != nullptr);
 }
 
 // ---- host-pointer entry points
 static int finish_bitmap(hs_ctx *c, size_t n, uint32_t *out_bitmap) {
   size_t words = (n + 31) / 32;
-  HS_CUDA(c, cudaMemcpyAsync(out_bitmap, c->d_out, words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out_bitmap, c->out.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
   HS_CUDA(c, cudaStreamSynchronize(c->stream));
   return HS_OK;
 }
@@ -333,11 +615,10 @@ int hs_verify_rec128(hs_ctx *c, const hs_rec128 *recs, size_t n, uint32_t mode, 
   if (n == 0) return HS_OK;
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
-  int rc;
-  if ((rc = ensure(c, &c->d_in, &c->d_in_cap, n * sizeof(hs_rec128)))) return rc;
-  if ((rc = ensure(c, &c->d_out, &c->d_out_cap, ((n + 31) / 32) * 4))) return rc;
-  HS_CUDA(c, cudaMemcpyAsync(c->d_in, recs, n * sizeof(hs_rec128), cudaMemcpyHostToDevice, c->stream));
-  if ((rc = hs_verify_rec128_dev(c, c->d_in, n, mode, c->d_out, c->stream))) return rc;
+  HS_TRY(ensure(c, c->in[0], n * sizeof(hs_rec128)));
+  HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
+  HS_CUDA(c, cudaMemcpyAsync(c->in[0].p, recs, n * sizeof(hs_rec128), cudaMemcpyHostToDevice, c->stream));
+  HS_TRY(run_verify(c, layout_rec128(c->in[0].p), n, mode, (uint32_t *)c->out.p, c->stream, false));
   return finish_bitmap(c, n, out_bitmap);
 }
 int hs_verify_strict_batch(hs_ctx *c, const hs_rec128 *recs, size_t n, uint32_t *out_bitmap) {
@@ -353,15 +634,15 @@ int hs_verify_var(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint8_
   HS_CUDA(c, cudaSetDevice(c->device));
   // device layout: [sig n*64][pk n*32][off (n+1)*8][msgs] — every section 8-byte aligned
   size_t o_sig = 0, o_pk = n * 64, o_off = o_pk + n * 32, o_msg = o_off + (n + 1) * 8, total = o_msg + off[n];
-  int rc;
-  if ((rc = ensure(c, &c->d_in, &c->d_in_cap, total + 8))) return rc;
-  if ((rc = ensure(c, &c->d_out, &c->d_out_cap, ((n + 31) / 32) * 4))) return rc;
-  uint8_t *d = (uint8_t *)c->d_in;
+  HS_TRY(ensure(c, c->in[0], total + 8));
+  HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
   HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig, n * 64, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(d + o_pk, pk, n * 32, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(d + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (off[n]) HS_CUDA(c, cudaMemcpyAsync(d + o_msg, msgs, off[n], cudaMemcpyHostToDevice, c->stream));
-  if ((rc = hs_verify_var_dev(c, d + o_sig, d + o_pk, d + o_msg, d + o_off, n, mode, c->d_out, c->stream))) return rc;
+  in_layout L{d + o_sig, 64, d + o_pk, 32, nullptr, d + o_msg, 0, nullptr, (const uint64_t *)(d + o_off), 0, 0};
+  HS_TRY(run_verify(c, L, n, mode, (uint32_t *)c->out.p, c->stream, false));
   return finish_bitmap(c, n, out_bitmap);
 }
 
@@ -375,71 +656,26 @@ int hs_verify_batch_shared_msg(hs_ctx *c, const uint8_t digest[32], const hs_vot
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   size_t words = (n + 31) / 32;
-  int rc;
-  if ((rc = ensure(c, &c->d_in, &c->d_in_cap, n * sizeof(hs_vote) + 32))) return rc;
-  if ((rc = ensure(c, &c->d_out, &c->d_out_cap, words * 4))) return rc;
-  uint8_t *d = (uint8_t *)c->d_in;
+  HS_TRY(ensure(c, c->in[0], n * sizeof(hs_vote) + 32));
+  HS_TRY(ensure(c, c->out, words * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
   HS_CUDA(c, cudaMemcpyAsync(d, digest, 32, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(d + 32, votes, n * sizeof(hs_vote), cudaMemcpyHostToDevice, c->stream));
-  var_layout L{d + 32 + 32, d + 32, d, nullptr, sizeof(hs_vote), sizeof(hs_vote), 32};
-  k_verify_var<<<blocks_for(n), HS_THREADS, 0, c->stream>>>(L, n, c->d_btable, HS_MODE_BATCH_EQ, (uint32_t *)c->d_out, nullptr);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
+  in_layout L{d + 32 + 32, sizeof(hs_vote), d + 32, sizeof(hs_vote), nullptr, d, 0, nullptr, nullptr, 32, 0};
+  HS_TRY(run_verify(c, L, n, HS_MODE_BATCH_EQ, (uint32_t *)c->out.p, c->stream, false));
+  std::vector<uint32_t> tmp;
   uint32_t *bm = out_bitmap_or_null;
-  uint32_t *tmp = nullptr;
   if (!bm) {
-    tmp = new (std::nothrow) uint32_t[words];
-    if (!tmp) return fail(c, HS_ERR_NOMEM, "host bitmap");
-    bm = tmp;
+    tmp.resize(words);
+    bm = tmp.data();
   }
-  rc = finish_bitmap(c, n, bm);
-  if (rc == HS_OK) {
-    int ok = 1;
-    for (size_t w = 0; w < words; w++) {
-      uint32_t want = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
-      if (bm[w] != want) ok = 0;
-    }
-    *all_ok = ok;
+  HS_TRY(finish_bitmap(c, n, bm));
+  int ok = 1;
+  for (size_t w = 0; w < words; w++) {
+    uint32_t want = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+    if (bm[w] != want) ok = 0;
   }
-  delete[] tmp;
-  return rc;
-}
-
-int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out_valid_bitmap) {
-  if (!c || (N && !pks)) return fail(c, HS_ERR_ARG, "hs_committee_register: bad argument");
-  std::lock_guard<std::mutex> g(c->mu);
-  HS_CUDA(c, cudaSetDevice(c->device));
-  HS_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaFree(c->d_pks);
-  cudaFree(c->d_key_flags);
-  cudaFree(c->d_atables);
-  c->d_pks = nullptr;
-  c->d_key_flags = nullptr;
-  c->d_atables = nullptr;
-  c->n_keys = 0;
-  if (N == 0) return HS_OK;
-  HS_CUDA(c, cudaMalloc(&c->d_pks, N * 32));
-  HS_CUDA(c, cudaMalloc(&c->d_key_flags, N));
-  HS_CUDA(c, cudaMalloc(&c->d_atables, N * sizeof(ge_niels) * HS_COMB_TABLE_NIELS));
-  HS_CUDA(c, cudaMemcpyAsync(c->d_pks, pks, N * 32, cudaMemcpyHostToDevice, c->stream));
-  k_build_comb<<<blocks_for(N * HS_COMB_WINDOWS), HS_THREADS, 0, c->stream>>>(c->d_pks, N, 1, c->d_atables, c->d_key_flags);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
-  HS_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->n_keys = N;
-  if (out_valid_bitmap) {
-    uint8_t *fl = new (std::nothrow) uint8_t[N];
-    if (!fl) return fail(c, HS_ERR_NOMEM, "host flags");
-    cudaError_t e = cudaMemcpy(fl, c->d_key_flags, N, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) {
-      delete[] fl;
-      return fail(c, HS_ERR_CUDA, "copy key flags", e);
-    }
-    for (size_t w = 0; w < (N + 31) / 32; w++) out_valid_bitmap[w] = 0;
-    for (size_t i = 0; i < N; i++)
-      if (fl[i] & 1) out_valid_bitmap[i >> 5] |= 1u << (i & 31);
-    delete[] fl;
-  }
+  *all_ok = ok;
   return HS_OK;
 }
 
@@ -454,15 +690,14 @@ int hs_verify_committee(hs_ctx *c, const uint32_t *vidx, const uint8_t *sig, con
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   size_t o_sig = 0, o_v = n * 64, o_m = o_v + n * 4, o_d = o_m + (midx ? n * 4 : 0), total = o_d + n_msgs * 32;
-  int rc;
-  if ((rc = ensure(c, &c->d_in, &c->d_in_cap, total))) return rc;
-  if ((rc = ensure(c, &c->d_out, &c->d_out_cap, ((n + 31) / 32) * 4))) return rc;
-  uint8_t *d = (uint8_t *)c->d_in;
+  HS_TRY(ensure(c, c->in[0], total));
+  HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
   HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig, n * 64, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(d + o_v, vidx, n * 4, cudaMemcpyHostToDevice, c->stream));
   if (midx) HS_CUDA(c, cudaMemcpyAsync(d + o_m, midx, n * 4, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(d + o_d, digests, n_msgs * 32, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = hs_verify_committee_dev(c, d + o_v, d + o_sig, midx ? d + o_m : nullptr, d + o_d, n, mode, c->d_out, c->stream))) return rc;
+  HS_TRY(hs_verify_committee_dev(c, d + o_v, d + o_sig, midx ? d + o_m : nullptr, d + o_d, n, mode, c->out.p, c->stream));
   return finish_bitmap(c, n, out_bitmap);
 }
 
@@ -473,16 +708,61 @@ int hs_digest32_batch(hs_ctx *c, const uint8_t *data, const uint64_t *off, size_
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   size_t o_off = 0, o_data = (n + 1) * 8, total = o_data + off[n];
-  int rc;
-  if ((rc = ensure(c, &c->d_in, &c->d_in_cap, total + 8))) return rc;
-  if ((rc = ensure(c, &c->d_out, &c->d_out_cap, n * 32))) return rc;
-  uint8_t *d = (uint8_t *)c->d_in;
+  HS_TRY(ensure(c, c->in[0], total + 8));
+  HS_TRY(ensure(c, c->out, n * 32));
+  uint8_t *d = (uint8_t *)c->in[0].p;
   HS_CUDA(c, cudaMemcpyAsync(d + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (off[n]) HS_CUDA(c, cudaMemcpyAsync(d + o_data, data, off[n], cudaMemcpyHostToDevice, c->stream));
-  if ((rc = hs_digest32_dev(c, d + o_data, d + o_off, n, c->d_out, c->stream))) return rc;
-  HS_CUDA(c, cudaMemcpyAsync(out, c->d_out, n * 32, cudaMemcpyDeviceToHost, c->stream));
+  HS_TRY(hs_digest32_dev(c, d + o_data, d + o_off, n, c->out.p, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out, c->out.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
   HS_CUDA(c, cudaStreamSynchronize(c->stream));
   return HS_OK;
+}
+
+// Reference-shaped end-to-end call: verdict_i = Signature::verify(Digest(msg_i), key_i) for fixed-size messages, with the
+// H2D copy of chunk j+1 overlapped with the kernels of chunk j (two streams, two staging buffers).
+int hs_verify_msgs(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint32_t *vidx, const uint8_t *msgs, size_t msg_len, size_t n,
+                   uint32_t mode, uint32_t *out_bitmap) {
+  if (!c || mode > 1 || (n && (!sig || (!pk && !vidx) || !msgs || !out_bitmap || msg_len == 0)))
+    return fail(c, HS_ERR_ARG, "hs_verify_msgs: bad argument");
+  if (n == 0) return HS_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  const size_t CH = 1u << 17;  // records per chunk (multiple of 32)
+  const size_t key_bytes = vidx ? 4 : 32;
+  const size_t per_rec = 64 + key_bytes + msg_len;
+  const size_t chunk_cap = (n < CH ? n : CH);
+  HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
+  // scratch shared by both chunks' verify passes is stream-ordered: verify of chunk j+1 is enqueued on the same compute
+  // stream after chunk j, only the copies run ahead on the second stream.
+  for (int b = 0; b < 2; b++) {
+    HS_TRY(ensure(c, c->in[b], chunk_cap * per_rec + 64));
+    HS_TRY(ensure(c, c->digest[b], chunk_cap * 32));
+  }
+  HS_TRY(ensure(c, c->xyz, chunk_cap * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, c->meta, chunk_cap));
+  if (!vidx && c->n_keys) {
+    HS_TRY(ensure(c, c->vidx, chunk_cap * 4));
+    HS_TRY(ensure(c, c->miss, chunk_cap * 4));
+  }
+  size_t nchunks = (n + CH - 1) / CH;
+  for (size_t j = 0; j < nchunks; j++) {
+    const int b = (int)(j & 1);
+    const size_t lo = j * CH, cnt = (n - lo < CH) ? (n - lo) : CH;
+    uint8_t *d = (uint8_t *)c->in[b].p;
+    const size_t o_sig = 0, o_key = cnt * 64, o_msg = o_key + ((cnt * key_bytes + 15) & ~(size_t)15);
+    if (j >= 2) HS_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_done[b], 0));  // staging buffer b is free again
+    HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig + lo * 64, cnt * 64, cudaMemcpyHostToDevice, c->stream2));
+    if (vidx) HS_CUDA(c, cudaMemcpyAsync(d + o_key, vidx + lo, cnt * 4, cudaMemcpyHostToDevice, c->stream2));
+    else HS_CUDA(c, cudaMemcpyAsync(d + o_key, pk + lo * 32, cnt * 32, cudaMemcpyHostToDevice, c->stream2));
+    HS_CUDA(c, cudaMemcpyAsync(d + o_msg, msgs + lo * msg_len, cnt * msg_len, cudaMemcpyHostToDevice, c->stream2));
+    HS_CUDA(c, cudaEventRecord(c->ev[b], c->stream2));
+    HS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[b], 0));
+    HS_TRY(hs_verify_msgs_dev(c, d + o_sig, vidx ? nullptr : d + o_key, vidx ? d + o_key : nullptr, d + o_msg, msg_len, cnt, mode,
+                              c->digest[b].p, (uint32_t *)c->out.p + lo / 32, c->stream));
+    HS_CUDA(c, cudaEventRecord(c->ev_done[b], c->stream));
+  }
+  return finish_bitmap(c, n, out_bitmap);
 }
 
 }  // extern "C"

@@ -132,6 +132,18 @@ class Engine:
         self._check(self.lib.hs_digest32_batch(self.h, _ptr(data) if data.size else None, _ptr(off), n, _ptr(out)), "hs_digest32_batch")
         return out
 
+    def verify_msgs(self, sig, msgs, msg_len, pk=None, validator_idx=None, mode=MODE_STRICT):
+        """Reference-shaped call: verdict_i = Signature::verify(Digest(msg_i), key_i); msgs = n fixed-size messages."""
+        sig = _u8(sig, 64).reshape(-1, 64)
+        n = sig.shape[0]
+        msgs = _u8(msgs)
+        assert msgs.size == n * msg_len and (pk is None) != (validator_idx is None)
+        pk = None if pk is None else _u8(pk, 32).reshape(-1, 32)
+        vidx = None if validator_idx is None else np.ascontiguousarray(validator_idx, dtype=np.uint32)
+        bm = np.zeros((n + 31) // 32, dtype=np.uint32)
+        self._check(self.lib.hs_verify_msgs(self.h, _ptr(sig), _ptr(pk), _ptr(vidx), _ptr(msgs), msg_len, n, mode, _ptr(bm)), "hs_verify_msgs")
+        return bitmap_to_bools(bm, n)
+
     # ---- device-resident API (torch tensors on this engine's device; enqueued on torch's current stream) -------
     @staticmethod
     def _stream():
@@ -149,6 +161,11 @@ class Engine:
         self._check(self.lib.hs_verify_committee_dev(self.h, d_vidx.data_ptr(), d_sig.data_ptr(), None if d_midx is None else d_midx.data_ptr(),
                                                      d_digests.data_ptr(), n, mode, d_bitmap.data_ptr(), self._stream()),
                     "hs_verify_committee_dev")
+
+    def verify_msgs_dev(self, d_sig, d_msgs, msg_len, d_digests, d_bitmap, n, d_pk=None, d_vidx=None, mode=MODE_STRICT):
+        self._check(self.lib.hs_verify_msgs_dev(self.h, d_sig.data_ptr(), None if d_pk is None else d_pk.data_ptr(),
+                                                None if d_vidx is None else d_vidx.data_ptr(), d_msgs.data_ptr(), msg_len, n, mode,
+                                                d_digests.data_ptr(), d_bitmap.data_ptr(), self._stream()), "hs_verify_msgs_dev")
 
     def digest32_dev(self, d_data, d_off, d_out, n):
         self._check(self.lib.hs_digest32_dev(self.h, d_data.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), self._stream()), "hs_digest32_dev")

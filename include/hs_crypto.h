@@ -77,7 +77,7 @@ int hs_verify_batch_shared_msg(hs_ctx *ctx, const uint8_t digest[32], const hs_v
                                uint32_t *out_bitmap_or_null);
 
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
-/* Decompresses every key and builds its comb table in HBM (384 KB per key).  out_valid_bitmap (nullable): bit i = key i
+/* Decompresses every key and builds its comb table in HBM (4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
 int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
 /* Vote i is (validator_idx[i], sig[i]) over digests[msg_idx[i]].  msg_idx may be NULL when n_msgs == 1. */
@@ -88,6 +88,13 @@ int hs_verify_committee(hs_ctx *ctx, const uint32_t *validator_idx, const uint8_
 /* Replaces Sha512::digest(..)[..32] at mempool/src/processor.rs:30 and consensus/src/messages.rs:81,151,203,270,308. */
 int hs_digest32_batch(hs_ctx *ctx, const uint8_t *data, const uint64_t *off, size_t n, uint8_t *out /* n x 32 */);
 
+/* ---- reference-shaped end-to-end call: verdict_i = Signature::verify(Digest(msg_i), key_i) ----------------------- */
+/* n fixed-size messages (msg_len bytes each, concatenated); key_i = pk[i] (pk != NULL) or committee key validator_idx[i].
+ * Computes the 32-byte Digest on the GPU (mempool/src/processor.rs:30 / consensus/src/messages.rs digests) and verifies
+ * over it, overlapping the host->device copy of one chunk with the kernels of the previous one. */
+int hs_verify_msgs(hs_ctx *ctx, const uint8_t *sig /* n x 64 */, const uint8_t *pk_or_null /* n x 32 */, const uint32_t *validator_idx_or_null,
+                   const uint8_t *msgs, size_t msg_len, size_t n, uint32_t mode, uint32_t *out_bitmap);
+
 /* ---- device-resident entry points (inputs already in HBM; enqueue on `stream`, a cudaStream_t) ------------------- */
 int hs_verify_rec128_dev(hs_ctx *ctx, const void *d_recs, size_t n, uint32_t mode, void *d_bitmap, void *stream);
 int hs_verify_var_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk, const void *d_msgs, const void *d_off, size_t n,
@@ -95,6 +102,9 @@ int hs_verify_var_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk, const vo
 int hs_verify_committee_dev(hs_ctx *ctx, const void *d_validator_idx, const void *d_sig, const void *d_msg_idx,
                             const void *d_digests, size_t n, uint32_t mode, void *d_bitmap, void *stream);
 int hs_digest32_dev(hs_ctx *ctx, const void *d_data, const void *d_off, size_t n, void *d_out, void *stream);
+/* d_digests: n x 32 bytes of scratch that receives Digest(msg_i). */
+int hs_verify_msgs_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk_or_null, const void *d_validator_idx_or_null, const void *d_msgs,
+                       size_t msg_len, size_t n, uint32_t mode, void *d_digests, void *d_bitmap, void *stream);
 
 #ifdef __cplusplus
 }

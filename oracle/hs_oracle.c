@@ -89,6 +89,24 @@ void hso_digest32(const uint8_t *msg, size_t len, uint8_t out[32]) {
 void hso_digest32_batch(const uint8_t *data, const uint64_t *off, size_t n, uint8_t *out) {
   for (size_t i = 0; i < n; i++) hso_digest32(data + off[i], (size_t)(off[i + 1] - off[i]), out + 32 * i);
 }
+typedef struct { const uint8_t *data; const uint64_t *off; uint8_t *out; size_t lo, hi; } djob_t;
+static void *djob_run(void *arg) {
+  djob_t *j = (djob_t *)arg;
+  for (size_t i = j->lo; i < j->hi; i++) hso_digest32(j->data + j->off[i], (size_t)(j->off[i + 1] - j->off[i]), j->out + 32 * i);
+  return NULL;
+}
+void hso_digest32_batch_mt(const uint8_t *data, const uint64_t *off, size_t n, int nthreads, uint8_t *out) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256]; djob_t jobs[256]; int started = 0; size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    size_t lo = (size_t)t * per, hi = lo + per; if (lo >= n) break; if (hi > n) hi = n;
+    jobs[t] = (djob_t){data, off, out, lo, hi};
+    if (nthreads == 1) djob_run(&jobs[t]); else pthread_create(&th[t], NULL, djob_run, &jobs[t]);
+    started++;
+  }
+  if (nthreads > 1) for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
 
 /* ------------------------------------------------------------------ GF(2^255-19), 5 x 51-bit limbs */
 typedef struct { uint64_t v[5]; } fe;

@@ -24,6 +24,7 @@ void hso_sha512(const uint8_t *msg, size_t len, uint8_t out[64]);
 void hso_digest32(const uint8_t *msg, size_t len, uint8_t out[32]);
 /* out[i] = digest32(data[off[i] .. off[i+1])) */
 void hso_digest32_batch(const uint8_t *data, const uint64_t *off, size_t n, uint8_t *out);
+void hso_digest32_batch_mt(const uint8_t *data, const uint64_t *off, size_t n, int nthreads, uint8_t *out);
 
 /* RFC 8032 5.1.5 / dalek Keypair::generate (crypto/src/lib.rs:167-175): pk from 32-byte seed. */
 void hso_keygen(const uint8_t seed[32], uint8_t pk[32]);

@@ -7,12 +7,25 @@
 #include "../../hotstuff_b200/csrc/verify_core.cuh"
 
 static std::vector<ge_niels> g_btable;
+static void build_table(std::vector<ge_niels> &t, const ge_ext &P, int W, int windows) {
+  const int entries = 1 << (W - 1), block = 64;
+  t.resize((size_t)windows * entries);
+  std::vector<fe> prod(block);
+  for (int w = 0; w < windows; w++)
+    for (int b = 0; b < entries / block; b++) comb_build_block(t.data(), P, W, w, b * block, block, prod.data());
+}
 static void ensure_btable() {
   if (!g_btable.empty()) return;
-  g_btable.resize(HS_COMB_TABLE_NIELS);
   ge_ext B;
   ge_basepoint(B);
-  for (int w = 0; w < HS_COMB_WINDOWS; w++) comb_build_window(g_btable.data(), B, w);
+  build_table(g_btable, B, HS_B_W, HS_B_WINDOWS);
+}
+static unsigned finish_one(const ge_ext &acc, const uint32_t (&R)[8], uint32_t meta) {
+  fe zinv;
+  ge_ext a = acc;
+  if (!(meta & HS_META_PARSE_OK)) { fe_set0(a.X); fe_set1(a.Y); fe_set1(a.Z); }
+  fe_invert(zinv, a.Z);
+  return verify_flags_from(a.X, a.Y, zinv, R, meta);
 }
 static void load_words(uint32_t (&w)[8], const uint8_t *p) { memcpy(w, p, 32); }
 
@@ -50,6 +63,8 @@ int emu_sc_digits(int W, int msb, const uint8_t s[32], int *out) {
   uint32_t w[8];
   load_words(w, s);
   if (W == 8) { digits_lsb<8> d; d.init(w); for (int i = 0; i < 32; i++) out[i] = d.next(); return 32; }
+  if (W == 12) { digits_lsb<12> d; d.init(w); for (int i = 0; i < sc_ndigits<12>(); i++) out[i] = d.next(); return sc_ndigits<12>(); }
+  if (W == 16) { digits_lsb<16> d; d.init(w); for (int i = 0; i < sc_ndigits<16>(); i++) out[i] = d.next(); return sc_ndigits<16>(); }
   if (W == 4 && msb) { digits_msb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[63 - i] = d.next(); return 64; }
   if (W == 4) { digits_lsb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[i] = d.next(); return 64; }
   return 0;
@@ -103,7 +118,9 @@ unsigned emu_verify_generic(const uint8_t sig[64], const uint8_t pk[32], const u
   emu_sha512_ram(sig, pk, msg, len, hb);
   memcpy(h, hb, 64);
   ge_cached tab[9];
-  return verify_generic_core(R, S, A, h, g_btable.data(), tab);
+  ge_ext acc;
+  uint32_t meta = verify_generic_main(acc, R, S, A, h, g_btable.data(), tab);
+  return finish_one(acc, R, meta);
 }
 // committee path: builds -A's comb table on the fly (slow; tests only)
 unsigned emu_verify_committee(const uint8_t sig[64], const uint8_t pk[32], const uint8_t *msg, uint64_t len) {
@@ -116,13 +133,15 @@ unsigned emu_verify_committee(const uint8_t sig[64], const uint8_t pk[32], const
   uint32_t a_ok = ge_decompress(Apt, A);
   uint32_t a_small = ge_enc_is_small_order(A);
   ge_neg(negA, Apt);
-  std::vector<ge_niels> at(HS_COMB_TABLE_NIELS);
-  if (a_ok) for (int w = 0; w < HS_COMB_WINDOWS; w++) comb_build_window(at.data(), negA, w);
-  else for (auto &q : at) ge_niels_identity(q);
+  std::vector<ge_niels> at;
+  if (!a_ok) ge_identity(negA);
+  build_table(at, negA, HS_A_W, HS_A_WINDOWS);
   uint8_t hb[64];
   emu_sha512_ram(sig, pk, msg, len, hb);
   memcpy(h, hb, 64);
-  return verify_committee_core(R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1));
+  ge_ext acc;
+  uint32_t meta = verify_committee_main(acc, R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1));
+  return finish_one(acc, R, meta);
 }
 const uint8_t *emu_btable_bytes(uint64_t *nbytes) {
   ensure_btable();

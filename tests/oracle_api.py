@@ -26,7 +26,7 @@ class Oracle:
         self.lib = L = ctypes.CDLL(path)
         L.hso_verify_flags.restype = ctypes.c_uint
         L.hso_verify_flags_fast.restype = ctypes.c_uint
-        for f in (L.hso_verify_rec128_batch, L.hso_verify_var_batch, L.hso_sign_batch, L.hso_keygen_batch, L.hso_digest32_batch):
+        for f in (L.hso_verify_rec128_batch, L.hso_verify_var_batch, L.hso_sign_batch, L.hso_keygen_batch, L.hso_digest32_batch, L.hso_digest32_batch_mt):
             f.restype = None
 
     def sha512(self, m):
@@ -97,14 +97,16 @@ class Oracle:
         ok = self.lib.hso_verify_batch_shared_msg(bytes(digest), _vp(votes), ctypes.c_size_t(n), int(nthreads), _vp(bm))
         return bool(ok), np.unpackbits(bm.view(np.uint8), bitorder="little")[:n].astype(bool)
 
-    def digest32_batch(self, data, off):
-        data = np.ascontiguousarray(np.frombuffer(bytes(data), dtype=np.uint8))
+    def digest32_batch(self, data, off, nthreads=1):
+        if isinstance(data, (bytes, bytearray, memoryview)):
+            data = np.frombuffer(bytes(data), dtype=np.uint8)
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
         if data.size == 0:
             data = np.zeros(1, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
         n = off.shape[0] - 1
         out = np.zeros((n, 32), dtype=np.uint8)
-        self.lib.hso_digest32_batch(_vp(data), _vp(off), ctypes.c_size_t(n), _vp(out))
+        self.lib.hso_digest32_batch_mt(_vp(data), _vp(off), ctypes.c_size_t(n), int(nthreads), _vp(out))
         return out
 
     # point helpers for adversarial fixtures

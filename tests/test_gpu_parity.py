@@ -199,3 +199,48 @@ def test_full_size_2pow20_properties(engine, oracle):
     want[bad] = oracle.verify_rec128(recs[bad])
     assert (got == want).all()
     assert got.sum() == n - (~want).sum()
+
+
+def test_registered_committee_lookup_mixed_with_unknown_keys(engine, oracle):
+    """With a committee registered, entry points that receive key BYTES resolve them on the device: registered keys take
+    the table path, unknown keys the generic path — same verdicts, including adversarial keys that collide in nothing."""
+    rng = np.random.default_rng(55)
+    w = make_workload(oracle, 3000, n_keys=64, seed=56, corrupt_frac=0.05)
+    recs = to_rec128(w)
+    engine.committee_register(w["pks"][:40])          # 24 of the 64 signer keys stay unknown
+    want = oracle.verify_rec128(recs)
+    assert (engine.verify_rec128(recs) == want).all()
+    assert (engine.verify_rec128(recs, mode=1) == oracle.verify_rec128(recs, mode=1)).all()
+    got = engine.verify_var(w["sig"], w["pk"], w["msgs"], w["off"])
+    assert (got == want).all()
+    # reference-shaped call with on-GPU Digest, both key forms
+    msgs = rng.integers(0, 256, (3000, 200), dtype=np.uint8)
+    d = oracle.digest32_batch(msgs.reshape(-1), np.arange(3001, dtype=np.uint64) * 200)
+    sig = oracle.sign_batch(w["seeds"], w["pks"], w["key_idx"], d.reshape(-1), np.arange(3001, dtype=np.uint64) * 32)
+    sig[::17, 3] ^= 0x40
+    want2 = oracle.verify_rec128(np.concatenate([sig, w["pks"][w["key_idx"]], d], axis=1))
+    assert (engine.verify_msgs(sig, msgs.reshape(-1), 200, pk=w["pks"][w["key_idx"]]) == want2).all()
+    engine.committee_register(w["pks"])
+    assert (engine.verify_msgs(sig, msgs.reshape(-1), 200, validator_idx=w["key_idx"]) == want2).all()
+    assert (engine.verify_msgs(sig, msgs.reshape(-1), 200, pk=w["pks"][w["key_idx"]]) == want2).all()
+    engine.committee_register(np.zeros((0, 32), np.uint8))   # clear the committee again for later tests
+    assert (engine.verify_rec128(recs) == want).all()
+
+
+def test_verify_msgs_chunked_pipeline(engine, oracle):
+    """hs_verify_msgs splits large calls into 2^17-record chunks on two streams; verdicts must not depend on the split."""
+    n = (1 << 17) * 2 + 777
+    base = make_workload(oracle, 2048, n_keys=2048, seed=91, msg_len=96)
+    reps = (n + 2047) // 2048
+    msgs = np.tile(base["msgs"].reshape(2048, 96), (reps, 1))[:n]
+    d = oracle.digest32_batch(base["msgs"], np.arange(2049, dtype=np.uint64) * 96)
+    sig_base = oracle.sign_batch(base["seeds"], base["pks"], base["key_idx"], d.reshape(-1), np.arange(2049, dtype=np.uint64) * 32)
+    sig = np.tile(sig_base, (reps, 1))[:n].copy()
+    pk = np.tile(base["pks"][base["key_idx"]], (reps, 1))[:n].copy()
+    rng = np.random.default_rng(92)
+    bad = rng.choice(n, 3000, replace=False)
+    sig[bad, rng.integers(0, 64, 3000)] ^= 1
+    got = engine.verify_msgs(sig, msgs.reshape(-1), 96, pk=pk)
+    want = np.ones(n, dtype=bool)
+    want[bad] = False
+    assert (got == want).all()

@@ -45,7 +45,7 @@ def test_scalar_reduce_and_recode(hostemu):
     for s in [0, 1, L_ORDER - 1, L_ORDER, L_ORDER + 1, 2**252, 2**253, 2**256 - 1]:
         assert hostemu.emu_sc_is_canonical(s.to_bytes(32, "little")) == (1 if s < L_ORDER else 0)
     edge = [0, L_ORDER - 1, 2**253 - 1, 2**252, int("7f" * 31, 16), int("80" * 31, 16), int("77" * 32, 16) % 2**253, int("88" * 32, 16) % 2**253]
-    for W, msb in ((8, 0), (4, 1), (4, 0)):
+    for W, msb in ((8, 0), (4, 1), (4, 0), (12, 0), (16, 0)):
         for s in edge + [int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**62)) ** 3 % L_ORDER for _ in range(200)]:
             out = (ctypes.c_int * 64)()
             n = hostemu.emu_sc_digits(W, msb, s.to_bytes(32, "little"), out)
