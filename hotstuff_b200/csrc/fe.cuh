@@ -94,36 +94,10 @@ HS_HD void fe_sqr(fe &r, const fe &a) {
 // ---------------------------------------------------------------- add / sub (result in [0, 2^256))
 HS_HD void fe_add(fe &r, const fe &a, const fe &b) {
 #if defined(__CUDA_ARCH__)
-  uint32_t t, u;
-  asm("{\n\t"
-      "add.cc.u32 %0, %10, %18;\n\t"
-      "addc.cc.u32 %1, %11, %19;\n\t"
-      "addc.cc.u32 %2, %12, %20;\n\t"
-      "addc.cc.u32 %3, %13, %21;\n\t"
-      "addc.cc.u32 %4, %14, %22;\n\t"
-      "addc.cc.u32 %5, %15, %23;\n\t"
-      "addc.cc.u32 %6, %16, %24;\n\t"
-      "addc.cc.u32 %7, %17, %25;\n\t"
-      "addc.u32 %8, 0, 0;\n\t"
-      "mul.lo.u32 %8, %8, 38;\n\t"
-      "add.cc.u32 %0, %0, %8;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
-      "addc.cc.u32 %2, %2, 0;\n\t"
-      "addc.cc.u32 %3, %3, 0;\n\t"
-      "addc.cc.u32 %4, %4, 0;\n\t"
-      "addc.cc.u32 %5, %5, 0;\n\t"
-      "addc.cc.u32 %6, %6, 0;\n\t"
-      "addc.cc.u32 %7, %7, 0;\n\t"
-      "addc.u32 %9, 0, 0;\n\t"
-      "mul.lo.u32 %9, %9, 38;\n\t"
-      "add.u32 %0, %0, %9;\n\t"
-      "}"
-      : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
-        "=&r"(r.v[7]), "=&r"(t), "=&r"(u)
-      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
-        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-  (void)t;
-  (void)u;
+  uint32_t t[8];
+  fe_add_asm(t, a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
 #else
   uint64_t acc = 0;
   uint32_t t[8];
@@ -145,36 +119,10 @@ HS_HD void fe_add(fe &r, const fe &a, const fe &b) {
 
 HS_HD void fe_sub(fe &r, const fe &a, const fe &b) {
 #if defined(__CUDA_ARCH__)
-  uint32_t t, u;
-  asm("{\n\t"
-      "sub.cc.u32 %0, %10, %18;\n\t"
-      "subc.cc.u32 %1, %11, %19;\n\t"
-      "subc.cc.u32 %2, %12, %20;\n\t"
-      "subc.cc.u32 %3, %13, %21;\n\t"
-      "subc.cc.u32 %4, %14, %22;\n\t"
-      "subc.cc.u32 %5, %15, %23;\n\t"
-      "subc.cc.u32 %6, %16, %24;\n\t"
-      "subc.cc.u32 %7, %17, %25;\n\t"
-      "subc.u32 %8, 0, 0;\n\t"
-      "and.b32 %8, %8, 38;\n\t"
-      "sub.cc.u32 %0, %0, %8;\n\t"
-      "subc.cc.u32 %1, %1, 0;\n\t"
-      "subc.cc.u32 %2, %2, 0;\n\t"
-      "subc.cc.u32 %3, %3, 0;\n\t"
-      "subc.cc.u32 %4, %4, 0;\n\t"
-      "subc.cc.u32 %5, %5, 0;\n\t"
-      "subc.cc.u32 %6, %6, 0;\n\t"
-      "subc.cc.u32 %7, %7, 0;\n\t"
-      "subc.u32 %9, 0, 0;\n\t"
-      "and.b32 %9, %9, 38;\n\t"
-      "sub.u32 %0, %0, %9;\n\t"
-      "}"
-      : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]),
-        "=&r"(r.v[7]), "=&r"(t), "=&r"(u)
-      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
-        "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-  (void)t;
-  (void)u;
+  uint32_t t[8];
+  fe_sub_asm(t, a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = t[i];
 #else
   int64_t acc = 0;
   uint32_t t[8];

@@ -102,6 +102,28 @@ HS_HD void ge_madd_p1p1(ge_p1p1 &c, const ge_ext &p, const ge_niels &q) {
   fe_sub(c.F, dd, t);
   fe_add(c.G, dd, t);
 }
+// r = p + (neg ? -q : q) without negating a field element: -q = (ymx, ypx, -xy2d), and -xy2d only swaps F and G.
+HS_HD void ge_madd_signed_p1p1(ge_p1p1 &c, const ge_ext &p, const ge_niels &q, uint32_t neg) {
+  fe a, b, t, dd, m0, m1;
+  fe_select(m0, q.ymx, q.ypx, neg);
+  fe_select(m1, q.ypx, q.ymx, neg);
+  fe_sub(t, p.Y, p.X);
+  fe_mul(a, t, m0);
+  fe_add(t, p.Y, p.X);
+  fe_mul(b, t, m1);
+  fe_mul(t, p.T, q.xy2d);
+  fe_add(dd, p.Z, p.Z);
+  fe_sub(c.E, b, a);
+  fe_add(c.H, b, a);
+  fe_sub(c.F, dd, t);
+  fe_add(c.G, dd, t);
+  fe_cswap(c.F, c.G, neg);
+}
+HS_HD void ge_madd_signed(ge_ext &r, const ge_ext &p, const ge_niels &q, uint32_t neg) {
+  ge_p1p1 c;
+  ge_madd_signed_p1p1(c, p, q, neg);
+  ge_p1p1_to_ext(r, c);
+}
 HS_HD void ge_madd(ge_ext &r, const ge_ext &p, const ge_niels &q) {
   ge_p1p1 c;
   ge_madd_p1p1(c, p, q);

@@ -128,6 +128,7 @@ struct committee_tables {
   const uint8_t *key_flags;
   uint32_t n_keys;
   const ge_niels *atables;
+  size_t table_entries;  // ge_niels per key
 };
 
 // Grid-stride over records so the same kernel serves a full launch (one pass) and the compacted miss list, whose length
@@ -135,13 +136,17 @@ struct committee_tables {
 template <bool COMMITTEE>
 __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
                                                              const uint32_t *__restrict__ index_list, const ge_niels *__restrict__ btable,
-                                                             committee_tables C, main_out O) {
-  __shared__ uint4 stage[HS_THREADS / 32][256];
+                                                             committee_tables C, main_out O, const comb_params cp) {
+  // one buffer, two lives: record staging while loading, then the signed digits [digit][thread] (conflict-free columns)
+  __shared__ __align__(16) unsigned char smem_raw[HS_MAX_DIGITS * HS_THREADS * 4];
+  static_assert(sizeof(smem_raw) >= (HS_THREADS / 32) * 256 * sizeof(uint4), "staging does not fit");
+  uint4(*stage)[256] = reinterpret_cast<uint4(*)[256]>(smem_raw);
+  int32_t *digits = reinterpret_cast<int32_t *>(smem_raw) + threadIdx.x;
   const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
   for (size_t base = (size_t)blockIdx.x * HS_THREADS; base < n; base += (size_t)gridDim.x * HS_THREADS) {
   const size_t t = base + threadIdx.x;
   const size_t warp_first = t & ~(size_t)31;
-  if (warp_first >= n) continue;
+  // (no early exit for warps past the end: every warp of the block reaches the barriers below; they clamp and do not store)
   const bool active = t < n;
   size_t i = active ? t : n - 1;
   uint32_t R[8], S[8], A[8], h[16];
@@ -149,7 +154,9 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(i
   bool have_key = true;
   if (L.aos128 && !index_list) {
     uint32_t M[8];
+    __syncthreads();  // the previous grid-stride iteration's digits live in the same shared bytes
     warp_load_rec128(R, S, A, M, reinterpret_cast<const uint4 *>(L.sig), n, warp_first, stage[threadIdx.x >> 5]);
+    __syncthreads();
     if (COMMITTEE) {
       v = __ldg(L.vidx + i);
       have_key = v < C.n_keys;
@@ -188,14 +195,15 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(i
   ge_ext acc;
   uint32_t meta;
   if (COMMITTEE) {
-    meta = verify_committee_main(acc, R, S, h, btable, C.atables + (size_t)v * HS_A_TABLE_NIELS, have_key ? C.key_flags[v] : 0u);
+    meta = verify_committee_main(acc, R, S, h, btable, C.atables + (size_t)v * C.table_entries, have_key ? C.key_flags[v] : 0u, digits,
+                                 HS_THREADS, cp);
     if (!have_key) {
       meta = HS_META_MISS;
       if (active && O.miss_list) O.miss_list[atomicAdd(O.miss_count, 1u)] = (uint32_t)i;
     }
   } else {
     ge_cached tab[9];
-    meta = verify_generic_main(acc, R, S, A, h, btable, tab);
+    meta = verify_generic_main(acc, R, S, A, h, btable, tab, digits, HS_THREADS, cp);
   }
   if (!active) continue;
   if (!(meta & HS_META_PARSE_OK)) {  // keep the batched inversion well-defined for rejected records
@@ -327,6 +335,9 @@ struct hs_ctx {
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   ge_niels *d_btable = nullptr;
+  comb_params cp{};
+  size_t a_table_entries = 0;
+  int wa_forced = 0;
   // committee
   size_t n_keys = 0;
   uint8_t *d_pks = nullptr;
@@ -395,7 +406,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
   HS_TRY(ensure(c, c->meta, n));
   main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, nullptr, nullptr};
-  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables};
+  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
   if (indexed && c->n_keys == 0) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (committee) {
@@ -410,19 +421,19 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
       O.miss_count = c->d_miss_count;
       HS_CUDA(c, cudaMemsetAsync(c->d_miss_count, 0, 4, stream));
     }
-    k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O);
+    k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
     if (!indexed) {
       // records whose key is not registered: generic path over the compacted list; the count stays on the device
       unsigned grid = blocks_for(n);
       if (grid > 148u * 4u) grid = 148u * 4u;
-      k_verify_main<false><<<grid, HS_THREADS, 0, stream>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O);
+      k_verify_main<false><<<grid, HS_THREADS, 0, stream>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O, c->cp);
       c->launches++;
       HS_CUDA(c, cudaGetLastError());
     }
   } else {
-    k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O);
+    k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
   }
@@ -440,9 +451,23 @@ static in_layout layout_rec128(const void *d_recs) {
 
 extern "C" {
 
+static void set_window(comb_params &cp, bool a, int w) {
+  if (a) {
+    cp.wa = w;
+    cp.na = sc_ndigits_rt(w);
+    sc_bias_rt(cp.bias_a, w);
+  } else {
+    cp.wb = w;
+    cp.nb = sc_ndigits_rt(w);
+    sc_bias_rt(cp.bias_b, w);
+  }
+}
+
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
-  (void)flags;
   if (!out) return HS_ERR_ARG;
+  int wb = (int)(flags & 0xffu);
+  if (wb == 0) wb = 24;  // 11 windows x 2^23 entries x 96 B = 8.9 GB of HBM for 11 instead of 16+ additions per [S]B
+  if (wb < 8 || wb > 24 || (wb % 2)) return HS_ERR_ARG;
   *out = nullptr;
   hs_ctx *c = new (std::nothrow) hs_ctx();
   if (!c) return HS_ERR_NOMEM;
@@ -456,9 +481,12 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
   if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
-  if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * HS_B_TABLE_NIELS);
+  set_window(c->cp, false, wb);
+  set_window(c->cp, true, 12);
+  c->wa_forced = (int)((flags >> 8) & 0xffu);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * comb_table_entries(wb));
   if (e == cudaSuccess) {
-    if (launch_build(c, nullptr, 1, 0, HS_B_W, HS_B_WINDOWS, c->d_btable, nullptr) != HS_OK) e = cudaGetLastError();
+    if (launch_build(c, nullptr, 1, 0, wb, c->cp.nb, c->d_btable, nullptr) != HS_OK) e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
@@ -540,11 +568,25 @@ int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out
   HS_CUDA(c, cudaMalloc(&c->d_pks, N * 32));
   HS_CUDA(c, cudaMalloc(&c->d_key_flags, N));
   HS_CUDA(c, cudaMalloc(&c->d_slots, (size_t)cap * 4));
-  cudaError_t e = cudaMalloc(&c->d_atables, N * sizeof(ge_niels) * HS_A_TABLE_NIELS);
+  // widest per-key window whose tables fit in ~45 % of the device (B200: 16 bits up to ~1.6 k keys, 14 up to ~5 k, 12 up to ~19 k)
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = total_b / 100 * 45;
+  if (budget > free_b - free_b / 8) budget = free_b - free_b / 8;
+  int wa = 8;
+  for (int w : {16, 14, 12, 10, 8}) {
+    if (c->wa_forced && w != c->wa_forced) continue;
+    wa = w;
+    if (N * comb_table_entries(w) * sizeof(ge_niels) <= budget) break;
+  }
+  if (sc_ndigits_rt(wa) + c->cp.nb > HS_MAX_DIGITS) return fail(c, HS_ERR_ARG, "window combination exceeds HS_MAX_DIGITS");
+  set_window(c->cp, true, wa);
+  c->a_table_entries = comb_table_entries(wa);
+  cudaError_t e = cudaMalloc(&c->d_atables, N * sizeof(ge_niels) * c->a_table_entries);
   if (e != cudaSuccess) return fail(c, HS_ERR_NOMEM, "committee tables do not fit in device memory", e);
   HS_CUDA(c, cudaMemcpyAsync(c->d_pks, pks, N * 32, cudaMemcpyHostToDevice, c->stream));
   HS_CUDA(c, cudaMemcpyAsync(c->d_slots, slots.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, c->stream));
-  HS_TRY(launch_build(c, c->d_pks, N, 1, HS_A_W, HS_A_WINDOWS, c->d_atables, c->d_key_flags));
+  HS_TRY(launch_build(c, c->d_pks, N, 1, wa, c->cp.na, c->d_atables, c->d_key_flags));
   HS_CUDA(c, cudaStreamSynchronize(c->stream));
   c->slot_mask = cap - 1;
   c->n_keys = N;

@@ -147,3 +147,38 @@ HS_HD int sc_digit(const sc_recoded<W> &r, int i) {
   uint32_t raw = (uint32_t)(two >> sh) & ((1u << W) - 1u);
   return (int)raw - (1 << (W - 1));
 }
+
+// ---- runtime-width variant (the comb tables' window widths are chosen per context / per committee size)
+HS_HD int sc_ndigits_rt(int W) {
+  int r = 253 % W;
+  return (253 + W - 1) / W + ((r == 0 || r == W - 1) ? 1 : 0);
+}
+// bias = sum_{i < ndigits} 2^(W-1 + W i); computed on the host once per table and passed to the kernels
+HS_HD void sc_bias_rt(uint32_t (&b)[9], int W) {
+  for (int i = 0; i < 9; i++) b[i] = 0;
+  const int n = sc_ndigits_rt(W);
+  for (int d = 0; d < n; d++) {
+    int bit = W - 1 + W * d;
+    b[bit >> 5] |= 1u << (bit & 31);
+  }
+}
+// dig[i * stride] = signed digit i of s in radix 2^W (i < n), each in [-2^(W-1), 2^(W-1) - 1]; W <= 24
+HS_HD void sc_digits_rt(int32_t *dig, int stride, const uint32_t (&s)[8], const uint32_t (&bias)[9], int W, int n) {
+  uint32_t u[9];
+  uint64_t acc = 0;
+  for (int i = 0; i < 9; i++) {
+    acc += (uint64_t)((i < 8) ? s[i] : 0u) + bias[i];
+    u[i] = (uint32_t)acc;
+    acc >>= 32;
+  }
+  const uint32_t mask = (1u << W) - 1u;
+  const int half = 1 << (W - 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < n; i++) {
+    dig[i * stride] = (int32_t)(u[0] & mask) - half;
+    for (int j = 0; j < 8; j++) u[j] = (u[j] >> W) | (u[j + 1] << (32 - W));
+    u[8] >>= W;
+  }
+}

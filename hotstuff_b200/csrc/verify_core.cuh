@@ -13,10 +13,10 @@
 //   strict   = eq and not small
 //
 // Scalar multiplication layout (B200-first, not dalek's vartime NAF — see DESIGN.md):
-//   [S]B      : radix-2^8 signed comb over a precomputed table of j * 256^i * B (32 windows x 128 affine-Niels
-//               entries, 384 KB, L2-resident) -> 32 mixed additions, no doublings.
-//   [k](-A)   : generic key  -> radix-2^4 signed fixed window, 8-entry per-thread table, 252 doublings + 64 additions;
-//               committee key -> the same comb as for B, over that validator's table in HBM -> 32 mixed additions.
+//   [S]B      : signed radix-2^w comb over a precomputed table of j * 2^(w i) * B, affine-Niels entries (96 B); no
+//               doublings.  w is chosen per context: 24 by default (11 windows, 8.8 GB of the 180 GB of HBM).
+//   [k](-A)   : committee key -> the same comb over that validator's own table (w = 16 / 14 / 12 by committee size);
+//               generic key   -> radix-2^4 signed fixed window, 8-entry per-thread table, 252 doublings + 64 additions.
 //   Every lane executes the same operation sequence (identity entry for digit 0), so warps never diverge.
 #pragma once
 #include <cstdint>
@@ -30,41 +30,20 @@
 #define HS_F_SMALL 8u
 #define HS_F_STRICT 16u
 
-// Comb window widths (bits).  B's table is shared by every signature and lives in L2 (16 x 32768 x 96 B = 48 MB);
-// each committee key gets its own table in HBM (22 x 2048 x 96 B = 4.1 MB per key; 10,000 validators = 41 GB of the
-// B200's 180 GB).  Wider windows trade HBM capacity / gather traffic for fewer field multiplications — the right trade
-// on a part whose integer-multiply pipe, not its memory system, is the binding resource.
-#ifndef HS_A_W
-#define HS_A_W 12
-#endif
-#ifndef HS_B_W
-#define HS_B_W 16
-#endif
-#define HS_A_WINDOWS (sc_ndigits<HS_A_W>())
-#define HS_B_WINDOWS (sc_ndigits<HS_B_W>())
-#define HS_A_ENTRIES (1 << (HS_A_W - 1))
-#define HS_B_ENTRIES (1 << (HS_B_W - 1))
-#define HS_A_TABLE_NIELS ((size_t)HS_A_WINDOWS * HS_A_ENTRIES)  // ge_niels per committee key
-#define HS_B_TABLE_NIELS ((size_t)HS_B_WINDOWS * HS_B_ENTRIES)
-
-// ---- digit streams over a recoded scalar (static register indexing: the scalar is shifted, not indexed)
-template <int W>
-struct digits_lsb {  // least-significant digit first
-  uint32_t u[9];
-  HS_HD void init(const uint32_t (&s)[8]) {
-    sc_recoded<W> r;
-    sc_recode<W>(r, s);
-    for (int i = 0; i < 9; i++) u[i] = r.u[i];
-  }
-  HS_HD int next() {
-    int d = (int)(u[0] & ((1u << W) - 1u)) - (1 << (W - 1));
-    for (int i = 0; i < 8; i++) u[i] = (u[i] >> W) | (u[i + 1] << (32 - W));
-    u[8] >>= W;
-    return d;
-  }
+// Comb window widths are runtime parameters: wider windows trade HBM capacity and gather traffic for fewer field
+// multiplications — the right trade on a part whose integer-multiply pipe, not its memory system, is the binding resource
+// (DESIGN.md §roofline).  Entries per window = 2^(w-1) (signed digits), windows = sc_ndigits_rt(w).
+struct comb_params {
+  int wa, na;  // committee-key tables: window width, number of windows
+  int wb, nb;  // base-point table
+  uint32_t bias_a[9], bias_b[9];
 };
+HS_HD size_t comb_table_entries(int w) { return (size_t)sc_ndigits_rt(w) << (w - 1); }
+#define HS_MAX_DIGITS 64  // >= na + nb for every supported (wa, wb) pair (wa, wb >= 8)
+
+// most-significant-digit-first stream over a radix-16 recoding (generic-key window method); W * ndigits must be 256
 template <int W>
-struct digits_msb {  // most-significant digit first; requires W * ndigits == 256
+struct digits_msb {
   uint32_t u[8];
   HS_HD void init(const uint32_t (&s)[8]) {
     static_assert(W * sc_ndigits<W>() == 256, "msb stream needs W | 256");
@@ -80,42 +59,83 @@ struct digits_msb {  // most-significant digit first; requires W * ndigits == 25
   }
 };
 
-// ---- table-entry loads
+// ---- table-entry loads: 96 B, 32 B-aligned -> six 16-byte loads (three full sectors)
+#if defined(__CUDA_ARCH__)
+#define HS_NIELS_UNPACK(q, a, b, c, d, e, f)                                                        \
+  q.ypx.v[0] = a.x; q.ypx.v[1] = a.y; q.ypx.v[2] = a.z; q.ypx.v[3] = a.w;                           \
+  q.ypx.v[4] = b.x; q.ypx.v[5] = b.y; q.ypx.v[6] = b.z; q.ypx.v[7] = b.w;                           \
+  q.ymx.v[0] = c.x; q.ymx.v[1] = c.y; q.ymx.v[2] = c.z; q.ymx.v[3] = c.w;                           \
+  q.ymx.v[4] = d.x; q.ymx.v[5] = d.y; q.ymx.v[6] = d.z; q.ymx.v[7] = d.w;                           \
+  q.xy2d.v[0] = e.x; q.xy2d.v[1] = e.y; q.xy2d.v[2] = e.z; q.xy2d.v[3] = e.w;                       \
+  q.xy2d.v[4] = f.x; q.xy2d.v[5] = f.y; q.xy2d.v[6] = f.z; q.xy2d.v[7] = f.w;
+#endif
 HS_HD void niels_load(ge_niels &q, const ge_niels *p) {
 #if defined(__CUDA_ARCH__)
-  // 96 B, 32 B-aligned: six 16-byte read-only loads (three full sectors)
   const uint4 *s = reinterpret_cast<const uint4 *>(p);
   uint4 a = __ldg(s + 0), b = __ldg(s + 1), c = __ldg(s + 2), d = __ldg(s + 3), e = __ldg(s + 4), f = __ldg(s + 5);
-  q.ypx.v[0] = a.x; q.ypx.v[1] = a.y; q.ypx.v[2] = a.z; q.ypx.v[3] = a.w;
-  q.ypx.v[4] = b.x; q.ypx.v[5] = b.y; q.ypx.v[6] = b.z; q.ypx.v[7] = b.w;
-  q.ymx.v[0] = c.x; q.ymx.v[1] = c.y; q.ymx.v[2] = c.z; q.ymx.v[3] = c.w;
-  q.ymx.v[4] = d.x; q.ymx.v[5] = d.y; q.ymx.v[6] = d.z; q.ymx.v[7] = d.w;
-  q.xy2d.v[0] = e.x; q.xy2d.v[1] = e.y; q.xy2d.v[2] = e.z; q.xy2d.v[3] = e.w;
-  q.xy2d.v[4] = f.x; q.xy2d.v[5] = f.y; q.xy2d.v[6] = f.z; q.xy2d.v[7] = f.w;
+  HS_NIELS_UNPACK(q, a, b, c, d, e, f)
+#else
+  q = *p;
+#endif
+}
+// streaming (evict-first) variant for the per-key tables: tens of GB of committee tables stream through L2
+HS_HD void niels_load_stream(ge_niels &q, const ge_niels *p) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *s = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldcs(s + 0), b = __ldcs(s + 1), c = __ldcs(s + 2), d = __ldcs(s + 3), e = __ldcs(s + 4), f = __ldcs(s + 5);
+  HS_NIELS_UNPACK(q, a, b, c, d, e, f)
 #else
   q = *p;
 #endif
 }
 
-// acc += sum_i digit_i(s) * 2^(W i) * P   using P's comb table (windows x 2^(W-1) affine Niels entries)
-template <int W>
-HS_HD void ge_comb_accumulate(ge_ext &acc, const ge_niels *table, const uint32_t (&s)[8]) {
-  constexpr int NW = sc_ndigits<W>();
-  constexpr int NE = 1 << (W - 1);
-  digits_lsb<W> ds;
-  ds.init(s);
+// acc += sum_i dig[i] * 2^(w i) * P using P's comb table; dig[] holds the signed digits (stride between digits)
+HS_HD void ge_comb_accumulate_rt(ge_ext &acc, const ge_niels *table, const int32_t *dig, int stride, int w, int n) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (int i = 0; i < NW; i++) {
-    int d = ds.next();
+  for (int i = 0; i < n; i++) {
+    int d = dig[i * stride];
     uint32_t neg = (uint32_t)(d < 0);
     int mag = d < 0 ? -d : d;
     ge_niels q;
     if (mag == 0) ge_niels_identity(q);
-    else niels_load(q, table + (size_t)i * NE + (mag - 1));
-    ge_niels_cneg(q, neg);
-    ge_madd(acc, acc, q);
+    else niels_load(q, table + ((size_t)i << (w - 1)) + (mag - 1));
+    ge_madd_signed(acc, acc, q, neg);
+  }
+}
+
+// acc = sum over the A windows of digit * 2^(wa i) * (-A)  +  sum over the B windows of digit * 2^(wb i) * B.
+// dig[0 .. na) are k's digits, dig[na .. na+nb) are S's.  ONE loop body (one copy of the mixed addition in the
+// instruction cache) with the table entry of iteration i+1 fetched while iteration i's addition executes.
+HS_HD void ge_comb_ab(ge_ext &acc, const ge_niels *atab, const ge_niels *btab, const int32_t *dig, int stride, const comb_params &cp) {
+  const int NA = cp.na, NT = cp.na + cp.nb;
+  ge_identity(acc);
+  ge_niels qn;
+  uint32_t negn;
+  {
+    int d = dig[0];
+    negn = (uint32_t)(d < 0);
+    int mag = d < 0 ? -d : d;
+    if (mag == 0) ge_niels_identity(qn);
+    else niels_load_stream(qn, atab + (mag - 1));
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < NT; i++) {
+    ge_niels q = qn;
+    const uint32_t neg = negn;
+    if (i + 1 < NT) {
+      const int j = i + 1;
+      int d = dig[j * stride];
+      negn = (uint32_t)(d < 0);
+      int mag = d < 0 ? -d : d;
+      if (mag == 0) ge_niels_identity(qn);
+      else if (j < NA) niels_load_stream(qn, atab + ((size_t)j << (cp.wa - 1)) + (mag - 1));
+      else niels_load(qn, btab + ((size_t)(j - NA) << (cp.wb - 1)) + (mag - 1));
+    }
+    ge_madd_signed(acc, acc, q, neg);
   }
 }
 
@@ -162,8 +182,10 @@ HS_HD void ge_scalarmult_window4(ge_ext &acc, const ge_ext &P, const uint32_t (&
 #define HS_META_SMALL 2u
 #define HS_META_MISS 0x80u  // committee lookup miss: record is re-run through the generic path
 
+// dig: thread-private digit slots (shared memory on the GPU: dig[i * dig_stride]), at least nb (generic) / na + nb entries
 HS_HD uint32_t verify_generic_main(ge_ext &acc, const uint32_t (&R)[8], const uint32_t (&S)[8], const uint32_t (&A)[8],
-                                   const uint32_t (&h)[16], const ge_niels *btable, ge_cached *tab) {
+                                   const uint32_t (&h)[16], const ge_niels *btable, ge_cached *tab, int32_t *dig, int dig_stride,
+                                   const comb_params &cp) {
   uint32_t k[8];
   sc_reduce512(k, h);
   uint32_t s_ok = sc_is_canonical(S);
@@ -172,19 +194,24 @@ HS_HD uint32_t verify_generic_main(ge_ext &acc, const uint32_t (&R)[8], const ui
   uint32_t small = ge_enc_is_small_order(R) | ge_enc_is_small_order(A);
   ge_neg(negA, Apt);
   ge_scalarmult_window4(acc, negA, k, tab);
-  ge_comb_accumulate<HS_B_W>(acc, btable, S);
+  sc_digits_rt(dig, dig_stride, S, cp.bias_b, cp.wb, cp.nb);
+  ge_comb_accumulate_rt(acc, btable, dig, dig_stride, cp.wb, cp.nb);
   return ((s_ok & a_ok) ? HS_META_PARSE_OK : 0u) | (small ? HS_META_SMALL : 0u);
 }
 // Committee key: -A's comb table was built at registration; a_flags bit0 = A decompressed, bit1 = A is small order.
 HS_HD uint32_t verify_committee_main(ge_ext &acc, const uint32_t (&R)[8], const uint32_t (&S)[8], const uint32_t (&h)[16],
-                                     const ge_niels *btable, const ge_niels *neg_a_table, uint32_t a_flags) {
-  uint32_t k[8];
-  sc_reduce512(k, h);
-  uint32_t s_ok = sc_is_canonical(S);
-  uint32_t small = ge_enc_is_small_order(R) | ((a_flags >> 1) & 1u);
-  ge_identity(acc);
-  ge_comb_accumulate<HS_A_W>(acc, neg_a_table, k);
-  ge_comb_accumulate<HS_B_W>(acc, btable, S);
+                                     const ge_niels *btable, const ge_niels *neg_a_table, uint32_t a_flags, int32_t *dig, int dig_stride,
+                                     const comb_params &cp) {
+  uint32_t s_ok, small;
+  {
+    uint32_t k[8];
+    sc_reduce512(k, h);
+    s_ok = sc_is_canonical(S);
+    small = ge_enc_is_small_order(R) | ((a_flags >> 1) & 1u);
+    sc_digits_rt(dig, dig_stride, k, cp.bias_a, cp.wa, cp.na);
+    sc_digits_rt(dig + cp.na * dig_stride, dig_stride, S, cp.bias_b, cp.wb, cp.nb);
+  }
+  ge_comb_ab(acc, neg_a_table, btable, dig, dig_stride, cp);
   return ((s_ok & a_flags & 1u) ? HS_META_PARSE_OK : 0u) | (small ? HS_META_SMALL : 0u);
 }
 
@@ -219,7 +246,7 @@ HS_HD void comb_build_block(ge_niels *table, const ge_ext &P, int W, int win, in
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (int b = 16; b >= 0; b--) {
+  for (int b = W; b >= 0; b--) {
     ge_dbl(m, m);
     if ((mult >> b) & 1) ge_add_cached(m, m, cb);
   }

@@ -35,10 +35,11 @@ def bitmap_to_bools(bitmap, n):
 
 
 class Engine:
-    def __init__(self, device=0):
+    def __init__(self, device=0, base_window=0, key_window=0):
+        """base_window / key_window: comb window widths in bits (0 = engine defaults: 24 and the widest that fits)."""
         self.lib = _lib.load()
         h = ctypes.c_void_p()
-        rc = self.lib.hs_ctx_create(ctypes.byref(h), int(device), 0)
+        rc = self.lib.hs_ctx_create(ctypes.byref(h), int(device), (int(base_window) & 0xff) | ((int(key_window) & 0xff) << 8))
         if rc != 0 or not h:
             raise EngineError("hs_ctx_create(device=%d) failed with status %d (no GPU / CUDA error); there is no CPU fallback" % (device, rc))
         self.h = h

@@ -50,7 +50,9 @@ typedef struct {
 } hs_vote;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
-/* device: CUDA ordinal.  Builds the base-point table on the GPU.  flags: reserved, pass 0. */
+/* device: CUDA ordinal.  Builds the base-point comb table on the GPU (default window 24 bits = 8.9 GB of HBM).
+ * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..24), bits 8-15 = forced per-key window width
+ * (8/10/12/14/16; 0 = widest that fits ~45 % of device memory). */
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
@@ -77,7 +79,7 @@ int hs_verify_batch_shared_msg(hs_ctx *ctx, const uint8_t digest[32], const hs_v
                                uint32_t *out_bitmap_or_null);
 
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
-/* Decompresses every key and builds its comb table in HBM (4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
+/* Decompresses every key and builds its comb table in HBM (w = 16: 48 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
 int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
 /* Vote i is (validator_idx[i], sig[i]) over digests[msg_idx[i]].  msg_idx may be NULL when n_msgs == 1. */

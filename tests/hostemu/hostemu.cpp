@@ -14,11 +14,21 @@ static void build_table(std::vector<ge_niels> &t, const ge_ext &P, int W, int wi
   for (int w = 0; w < windows; w++)
     for (int b = 0; b < entries / block; b++) comb_build_block(t.data(), P, W, w, b * block, block, prod.data());
 }
+static comb_params g_cp;
+// window widths used by the host emulation (small enough to build on a CPU; the logic is width-independent)
+extern "C" void emu_set_windows(int wa, int wb) {
+  g_cp.wa = wa; g_cp.na = sc_ndigits_rt(wa);
+  g_cp.wb = wb; g_cp.nb = sc_ndigits_rt(wb);
+  sc_bias_rt(g_cp.bias_a, wa);
+  sc_bias_rt(g_cp.bias_b, wb);
+  g_btable.clear();
+}
 static void ensure_btable() {
+  if (g_cp.wa == 0) emu_set_windows(10, 12);
   if (!g_btable.empty()) return;
   ge_ext B;
   ge_basepoint(B);
-  build_table(g_btable, B, HS_B_W, HS_B_WINDOWS);
+  build_table(g_btable, B, g_cp.wb, g_cp.nb);
 }
 static unsigned finish_one(const ge_ext &acc, const uint32_t (&R)[8], uint32_t meta) {
   fe zinv;
@@ -58,16 +68,18 @@ int emu_sc_is_canonical(const uint8_t s[32]) {
   load_words(w, s);
   return (int)sc_is_canonical(w);
 }
-// digits of the signed recoding, W in {4, 8}; returns count
+// digits of the signed recoding: W == 4 with msb != 0 uses the radix-16 msb stream, everything else the runtime recoder
 int emu_sc_digits(int W, int msb, const uint8_t s[32], int *out) {
   uint32_t w[8];
   load_words(w, s);
-  if (W == 8) { digits_lsb<8> d; d.init(w); for (int i = 0; i < 32; i++) out[i] = d.next(); return 32; }
-  if (W == 12) { digits_lsb<12> d; d.init(w); for (int i = 0; i < sc_ndigits<12>(); i++) out[i] = d.next(); return sc_ndigits<12>(); }
-  if (W == 16) { digits_lsb<16> d; d.init(w); for (int i = 0; i < sc_ndigits<16>(); i++) out[i] = d.next(); return sc_ndigits<16>(); }
   if (W == 4 && msb) { digits_msb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[63 - i] = d.next(); return 64; }
-  if (W == 4) { digits_lsb<4> d; d.init(w); for (int i = 0; i < 64; i++) out[i] = d.next(); return 64; }
-  return 0;
+  uint32_t bias[9];
+  sc_bias_rt(bias, W);
+  int n = sc_ndigits_rt(W);
+  int32_t dig[80];
+  sc_digits_rt(dig, 1, w, bias, W, n);
+  for (int i = 0; i < n; i++) out[i] = dig[i];
+  return n;
 }
 void emu_sha512(const uint8_t *msg, uint64_t len, uint8_t out[64]) {
   uint32_t o[16];
@@ -119,7 +131,8 @@ unsigned emu_verify_generic(const uint8_t sig[64], const uint8_t pk[32], const u
   memcpy(h, hb, 64);
   ge_cached tab[9];
   ge_ext acc;
-  uint32_t meta = verify_generic_main(acc, R, S, A, h, g_btable.data(), tab);
+  int32_t dig[HS_MAX_DIGITS];
+  uint32_t meta = verify_generic_main(acc, R, S, A, h, g_btable.data(), tab, dig, 1, g_cp);
   return finish_one(acc, R, meta);
 }
 // committee path: builds -A's comb table on the fly (slow; tests only)
@@ -135,12 +148,13 @@ unsigned emu_verify_committee(const uint8_t sig[64], const uint8_t pk[32], const
   ge_neg(negA, Apt);
   std::vector<ge_niels> at;
   if (!a_ok) ge_identity(negA);
-  build_table(at, negA, HS_A_W, HS_A_WINDOWS);
+  build_table(at, negA, g_cp.wa, g_cp.na);
   uint8_t hb[64];
   emu_sha512_ram(sig, pk, msg, len, hb);
   memcpy(h, hb, 64);
   ge_ext acc;
-  uint32_t meta = verify_committee_main(acc, R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1));
+  int32_t dig[HS_MAX_DIGITS];
+  uint32_t meta = verify_committee_main(acc, R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1), dig, 1, g_cp);
   return finish_one(acc, R, meta);
 }
 const uint8_t *emu_btable_bytes(uint64_t *nbytes) {

@@ -244,3 +244,33 @@ def test_verify_msgs_chunked_pipeline(engine, oracle):
     want = np.ones(n, dtype=bool)
     want[bad] = False
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("base_window,key_window", [(8, 8), (12, 10), (16, 12), (20, 14), (24, 16)])
+def test_window_width_independence(oracle, golden, base_window, key_window):
+    """Verdicts must not depend on the comb window widths (table sizes): golden vectors + a random set, generic and
+    committee paths, for the small / medium / default table geometries."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hotstuff_b200 import Engine
+    e = Engine(0, base_window=base_window, key_window=key_window)
+    try:
+        vs, sig, pk, msgs = _golden_arrays(golden, only32=True)
+        recs = np.concatenate([sig, pk, np.array([np.frombuffer(m, np.uint8) for m in msgs])], axis=1)
+        got = e.verify_rec128(recs)
+        for v, a in zip(vs, got):
+            assert bool(a) == v["strict"], v["name"]
+        w = make_workload(oracle, 2000, n_keys=37, seed=300 + base_window, corrupt_frac=0.05)
+        r = to_rec128(w)
+        want = oracle.verify_rec128(r)
+        assert (e.verify_rec128(r) == want).all()
+        assert e.committee_register(w["pks"]).all()
+        assert (e.verify_rec128(r) == want).all()                      # lookup path
+        keys, inv = np.unique(pk, axis=0, return_inverse=True)
+        e.committee_register(keys)
+        got = e.verify_committee(inv.astype(np.uint32), sig, recs[:, 96:], msg_idx=np.arange(len(vs), dtype=np.uint32))
+        for v, a in zip(vs, got):
+            assert bool(a) == v["strict"], v["name"]
+    finally:
+        e.close()

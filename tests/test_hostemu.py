@@ -45,9 +45,9 @@ def test_scalar_reduce_and_recode(hostemu):
     for s in [0, 1, L_ORDER - 1, L_ORDER, L_ORDER + 1, 2**252, 2**253, 2**256 - 1]:
         assert hostemu.emu_sc_is_canonical(s.to_bytes(32, "little")) == (1 if s < L_ORDER else 0)
     edge = [0, L_ORDER - 1, 2**253 - 1, 2**252, int("7f" * 31, 16), int("80" * 31, 16), int("77" * 32, 16) % 2**253, int("88" * 32, 16) % 2**253]
-    for W, msb in ((8, 0), (4, 1), (4, 0), (12, 0), (16, 0)):
+    for W, msb in ((4, 1), (4, 0), (8, 0), (10, 0), (11, 0), (12, 0), (14, 0), (16, 0), (20, 0), (23, 0), (24, 0)):
         for s in edge + [int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**62)) ** 3 % L_ORDER for _ in range(200)]:
-            out = (ctypes.c_int * 64)()
+            out = (ctypes.c_int * 80)()
             n = hostemu.emu_sc_digits(W, msb, s.to_bytes(32, "little"), out)
             d = list(out)[:n]
             assert all(-(1 << (W - 1)) <= x < (1 << (W - 1)) for x in d)
@@ -87,7 +87,12 @@ def test_decompress_and_small_order(hostemu, oracle, golden):
         assert hostemu.emu_enc_is_small_order(e) == (1 if so == 1 else 0) or so == -1 and not ok, e.hex()
 
 
-def test_golden_vectors_generic_and_committee_paths(hostemu, golden):
+import pytest
+
+
+@pytest.mark.parametrize("wa,wb", [(10, 12), (8, 8), (12, 16)])
+def test_golden_vectors_generic_and_committee_paths(hostemu, golden, wa, wb):
+    hostemu.emu_set_windows(wa, wb)
     for v in golden["vectors"]:
         sig, pk, msg = bytes.fromhex(v["sig"]), bytes.fromhex(v["pk"]), bytes.fromhex(v["msg"])
         want = v["flags"] & ~R_OK

@@ -30,14 +30,29 @@ class Prog:
         self.ops.append((op, dst, list(srcs)))
 
     # ---- simulation -----------------------------------------------------
-    def run(self, env):
+    def run(self, env, trace=None):
         cc = 0
         env = dict(env)
 
         def val(x):
             return x if isinstance(x, int) else env[x]
 
-        for op, dst, srcs in self.ops:
+        labels = {dst: i for i, (op, dst, _) in enumerate(self.ops) if op == "label"}
+        pc = 0
+        while pc < len(self.ops):
+            op, dst, srcs = self.ops[pc]
+            pc += 1
+            if op == "label":
+                continue
+            if op == "setp.lt.u32":
+                env[dst] = 1 if val(srcs[0]) < val(srcs[1]) else 0
+                continue
+            if op == "bra_if_not":        # dst = predicate, srcs[0] = label: the common (fall-through-skipping) path
+                if not env[dst]:
+                    pc = labels[srcs[0]]
+                elif trace is not None:
+                    trace.add(srcs[0])
+                continue
             s = [val(x) for x in srcs]
             base = op.replace(".u32", "")
             if base in ("mul.lo", "mul.hi"):
@@ -76,13 +91,19 @@ class Prog:
         temps = []
         seen = set()
         for op, dst, srcs in self.ops:
-            for r in [dst] + [x for x in srcs if not isinstance(x, int)]:
+            if op == "label":
+                continue
+            for r in [dst] + [x for x in srcs if not isinstance(x, int) and not str(x).startswith("L_")]:
                 if r not in operand and r not in seen:
                     seen.add(r)
                     temps.append(r)
+        preds = [t for t in temps if t.startswith("p_")]
+        temps = [t for t in temps if not t.startswith("p_") and not t.startswith("L_")]
         lines = ["{"]
         for i in range(0, len(temps), 12):
             lines.append(".reg .u32 " + ", ".join(temps[i:i + 12]) + ";")
+        if preds:
+            lines.append(".reg .pred " + ", ".join(preds) + ";")
 
         def o(x):
             if isinstance(x, int):
@@ -90,7 +111,13 @@ class Prog:
             return operand.get(x, x)
 
         for op, dst, srcs in self.ops:
-            if op.startswith("shf.l"):
+            if op == "label":
+                lines.append("%s:" % dst)
+            elif op == "bra_if_not":
+                lines.append("@!%s bra %s;" % (dst, srcs[0]))
+            elif op == "setp.lt.u32":
+                lines.append("setp.lt.u32 %s, %s, %s;" % (dst, o(srcs[0]), o(srcs[1])))
+            elif op.startswith("shf.l"):
                 lines.append("shf.l.clamp.b32 %s, %s, %s, %s;" % (o(dst), o(srcs[0]), o(srcs[1]), o(srcs[2])))
             elif op.startswith("and"):
                 lines.append("and.b32 %s, %s, %s;" % (o(dst), o(srcs[0]), o(srcs[1])))
@@ -127,8 +154,25 @@ def chain_row(pr, arr, defined, ai, terms, first_free):
         defined.add(k)
 
 
+def gen_fold_top(pr, c, top, tag):
+    """c[0..7] += 38 * top (top < 2^7) with the carry ripple out of limb 0 — probability ~2^-21 — taken out of line."""
+    pr.emit("mul.lo.u32", top, top, 38)
+    pr.emit("add.u32", c[0], c[0], top)
+    pr.emit("setp.lt.u32", "p_" + tag, c[0], top)          # wrapped  <=>  sum < addend
+    pr.emit("bra_if_not", "p_" + tag, "L_" + tag)
+    pr.emit("add.cc.u32", c[1], c[1], 1)
+    for k in range(2, 8):
+        pr.emit("addc.cc.u32", c[k], c[k], 0)
+    pr.emit("addc.u32", "w_" + tag, 0, 0)
+    # a second wrap leaves a value < 2^13 in c, so +38 cannot carry again
+    pr.emit("mul.lo.u32", "w_" + tag, "w_" + tag, 38)
+    pr.emit("add.u32", c[0], c[0], "w_" + tag)
+    pr.emit("label", "L_" + tag)
+
+
 def gen_reduce(pr, c, out):
-    """c[0..15] (names) -> out[0..7], value = c mod p in [0, 2^256)."""
+    """c[0..15] (names) -> value = c mod p in [0, 2^256), left in c[0..7] (which must be the output names)."""
+    assert list(c[:8]) == list(out)
     # even columns: (c0,c1) += 38*c8 ; (c2,c3) += 38*c10 ; ...
     first = True
     for j in (0, 2, 4, 6):
@@ -144,25 +188,17 @@ def gen_reduce(pr, c, out):
     for k in range(2, 8):
         pr.emit("addc.cc.u32", c[k], c[k], "q%d" % k)
     pr.emit("addc.u32", "t8", "t8", "q8")
-    # fold the 9th limb (< 2^7): c += 38*t8
-    pr.emit("mul.lo.u32", "t8", "t8", 38)
-    pr.emit("add.cc.u32", c[0], c[0], "t8")
-    for k in range(1, 8):
-        pr.emit("addc.cc.u32", c[k], c[k], 0)
-    pr.emit("addc.u32", "t9", 0, 0)
-    # a second wrap leaves a value < 2^13 in c, so +38 cannot carry
-    pr.emit("mul.lo.u32", "t9", "t9", 38)
-    pr.emit("add.u32", out[0], c[0], "t9")
-    for k in range(1, 8):
-        if out[k] != c[k]:
-            pr.emit("add.u32", out[k], c[k], 0)
+    gen_fold_top(pr, c, "t8", "red")
 
 
 def gen_mul():
     pr = Prog()
     a = ["a%d" % i for i in range(8)]
     b = ["b%d" % i for i in range(8)]
-    E, O = "e%d", "o%d"      # o[k] holds column k+1
+    class Names:                      # even accumulators 0..7 are the outputs themselves (no copy at the end)
+        def __mod__(self, k):
+            return ("r%d" % k) if k < 8 else ("e%d" % k)
+    E, O = Names(), "o%d"      # o[k] holds column k+1
     de, do = set(), set()
     for i in range(8):
         te = [(i + j, b[j]) for j in range(8) if (i + j) % 2 == 0]
@@ -179,7 +215,7 @@ def gen_mul():
         chain_row(pr, O, do, a[i], to, 15)
     assert de == set(range(16)) and do == set(range(15)), (de, do)
     # merge: c[k] = e[k] + o[k-1]
-    pr.emit("add.cc.u32", "e1", "e1", "o0")
+    pr.emit("add.cc.u32", E % 1, E % 1, "o0")
     for k in range(2, 15):
         pr.emit("addc.cc.u32", E % k, E % k, O % (k - 1))
     pr.emit("addc.u32", "e15", "e15", "o14")
@@ -213,7 +249,7 @@ def gen_sqr():
     for k in range(16):
         ek = (E % k) if k in de else None
         ok = (O % (k - 1)) if (k - 1) in do else None
-        name = "c%d" % k
+        name = ("r%d" % k) if k < 8 else ("c%d" % k)
         if ek is None and ok is None:
             pr.emit("add.u32", name, 0, 0) if first else pr.emit("addc.cc.u32", name, 0, 0)
         elif first:
@@ -235,6 +271,80 @@ def gen_sqr():
         pr.emit("madc.hi.cc.u32", c[2 * i + 1], a[i], a[i], c[2 * i + 1])
     gen_reduce(pr, c, ["r%d" % k for k in range(8)])
     return pr
+
+
+def gen_add():
+    """r = a + b mod p (result in [0, 2^256)): 8-limb add, fold the carry as +38, rare second ripple out of line."""
+    pr = Prog()
+    pr.emit("add.cc.u32", "r0", "a0", "b0")
+    for k in range(1, 8):
+        pr.emit("addc.cc.u32", "r%d" % k, "a%d" % k, "b%d" % k)
+    pr.emit("addc.u32", "t8", 0, 0)
+    gen_fold_top(pr, ["r%d" % k for k in range(8)], "t8", "add")
+    return pr
+
+
+def gen_sub():
+    """r = a - b mod p: 8-limb subtract, fold the borrow as -38, rare second ripple out of line."""
+    pr = Prog()
+    pr.emit("sub.cc.u32", "r0", "a0", "b0")
+    for k in range(1, 8):
+        pr.emit("subc.cc.u32", "r%d" % k, "a%d" % k, "b%d" % k)
+    pr.emit("subc.u32", "t8", 0, 0)              # 0 or 0xffffffff
+    pr.emit("and", "t8", "t8", 38)
+    pr.emit("setp.lt.u32", "p_sub", "r0", "t8")  # the -38 borrows out of limb 0 (probability ~2^-27)
+    pr.emit("sub.u32", "r0", "r0", "t8")
+    pr.emit("bra_if_not", "p_sub", "L_sub")
+    pr.emit("sub.cc.u32", "r1", "r1", 1)
+    for k in range(2, 8):
+        pr.emit("subc.cc.u32", "r%d" % k, "r%d" % k, 0)
+    pr.emit("subc.u32", "w_sub", 0, 0)
+    pr.emit("and", "w_sub", "w_sub", 38)
+    pr.emit("sub.u32", "r0", "r0", "w_sub")      # after a second wrap the value is >= 2^256-38: no further borrow
+    pr.emit("label", "L_sub")
+    return pr
+
+
+def check_addsub(pr, is_sub):
+    rnd = random.Random(99)
+    top = (1 << 256) - 1
+    specials = [0, 1, 37, 38, 39, P - 1, P, P + 1, 2 * P, 2 * P + 1, top, top - 37, top - 38, (1 << 255), M32, M32 - 37, (top ^ M32), (top ^ M32) + 5,
+                (1 << 32), (1 << 32) + 37, (1 << 224)]
+    cases = [(x, y) for x in specials for y in specials]
+    for _ in range(4000):
+        x, y = rnd.getrandbits(256), rnd.getrandbits(256)
+        if rnd.random() < 0.3:
+            y = (top - x + rnd.randrange(-60, 60)) & top if not is_sub else (x + rnd.randrange(-60, 60)) & top
+        cases.append((x, y))
+    trace = set()
+    for x, y in cases:
+        env = {"a%d" % i: v for i, v in enumerate(limbs(x))}
+        env.update({"b%d" % i: v for i, v in enumerate(limbs(y))})
+        out = pr.run(env, trace)
+        r = sum(out["r%d" % i] << (32 * i) for i in range(8))
+        assert r < (1 << 256) and r % P == ((x - y) if is_sub else (x + y)) % P, (hex(x), hex(y), hex(r))
+    assert trace, "rare path never exercised"
+
+
+def check_reduce():
+    """gen_reduce on arbitrary 512-bit inputs, including ones built to hit the out-of-line ripple."""
+    pr = Prog()
+    c = ["r%d" % k for k in range(8)] + ["e%d" % k for k in range(8, 16)]
+    gen_reduce(pr, c, c[:8])
+    rnd = random.Random(7)
+    trace = set()
+    cases = [rnd.getrandbits(512) for _ in range(3000)] + [(1 << 512) - 1, 0, (1 << 256) - 1, ((1 << 256) - 1) << 256]
+    for _ in range(3000):   # low limb close to wrapping after the fold, upper limbs all ones -> long ripple
+        hi = rnd.getrandbits(256)
+        lo_target = ((1 << 256) - rnd.randrange(1, 3000)) & ((1 << 256) - 1)
+        lo = (lo_target - 38 * hi) % (1 << 256)
+        cases.append((hi << 256) | lo)
+    for v in cases:
+        env = {name: (v >> (32 * k)) & M32 for k, name in enumerate(c)}
+        out = pr.run(env, trace)
+        r = sum(out["r%d" % i] << (32 * i) for i in range(8))
+        assert r < (1 << 256) and r % P == v % P, hex(v)
+    assert "L_red" in trace, "reduce ripple never exercised"
 
 
 def limbs(v, n=8):
@@ -265,6 +375,7 @@ def check(pr, is_sqr):
 
 
 def emit_function(name, pr, nin):
+    # asm volatile is not needed: the block has no side effects beyond its outputs
     operand = {}
     idx = 0
     for k in range(8):
@@ -296,11 +407,16 @@ if __name__ == "__main__":
     m, s = gen_mul(), gen_sqr()
     check(m, False)
     check(s, True)
+    check_reduce()
+    ad, sb = gen_add(), gen_sub()
+    check_addsub(ad, False)
+    check_addsub(sb, True)
     hdr = ("// GENERATED by tools/gen_fe_asm.py — do not edit.\n"
            "// GF(2^255-19) multiply / square on 8 saturated 32-bit limbs; mad.lo.cc/madc.hi.cc pairs fuse to IMAD.WIDE.U32.X.\n"
            "// Every sequence below was simulated against Python big integers by the generator before being emitted.\n"
            "#pragma once\n#include <cstdint>\n\n")
-    txt = hdr + emit_function("fe_mul_asm", m, 2) + "\n" + emit_function("fe_sqr_asm", s, 1)
+    txt = (hdr + emit_function("fe_mul_asm", m, 2) + "\n" + emit_function("fe_sqr_asm", s, 1) + "\n" +
+           emit_function("fe_add_asm", ad, 2) + "\n" + emit_function("fe_sub_asm", sb, 2))
     path = os.path.join(ROOT, "hotstuff_b200", "csrc", "fe_asm.cuh")
     open(path, "w").write(txt)
     print("mul: %d wide-mads + %d other ops; sqr: %d wide-mads + %d other ops -> %s" % (count(m) + count(s) + (path,)))
