@@ -3,7 +3,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libhs_crypto.so")
+LIB_PATH = os.environ.get("HS_CRYPTO_LIB") or os.path.join(PKG, "libhs_crypto.so")  # env override: kernel-variant experiments
 
 c_void_p, c_size_t, c_u32, c_int, c_u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint64
 

@@ -93,7 +93,8 @@ __host__ __device__ inline uint32_t key_hash(const uint32_t *w) {
   }
   return h;
 }
-__global__ void __launch_bounds__(256) k_key_lookup(in_layout L, size_t n, key_table T, uint32_t *__restrict__ out_vidx) {
+__global__ void __launch_bounds__(256) k_key_lookup(in_layout L, size_t n, key_table T, uint32_t *__restrict__ out_vidx,
+                                                    uint32_t *__restrict__ miss_list, uint32_t *__restrict__ miss_count) {
   const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   uint32_t k[8];
@@ -114,14 +115,14 @@ __global__ void __launch_bounds__(256) k_key_lookup(in_layout L, size_t n, key_t
     h = (h + 1) & T.mask;
   }
   out_vidx[i] = found;
+  if (found == HS_NO_KEY) miss_list[atomicAdd(miss_count, 1u)] = (uint32_t)i;  // compacted list for the generic pass
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1: main
 struct main_out {
   fe *xyz;         // 3 field elements per record: X, Y, Z of R' = [S]B + [k](-A)
   uint8_t *meta;   // HS_META_* per record
-  uint32_t *miss_list;
-  uint32_t *miss_count;
+  int side_pass;   // 1: records without a registered key are handled by the concurrent generic pass
 };
 struct committee_tables {
   const uint8_t *pks;
@@ -134,7 +135,10 @@ struct committee_tables {
 // Grid-stride over records so the same kernel serves a full launch (one pass) and the compacted miss list, whose length
 // only the device knows (n_ptr): no host round trip between the committee pass and the generic pass.
 template <bool COMMITTEE>
-__global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
+#ifndef HS_MAIN_MINBLOCKS
+#define HS_MAIN_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : 3) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
                                                              const uint32_t *__restrict__ index_list, const ge_niels *__restrict__ btable,
                                                              committee_tables C, main_out O, const comb_params cp) {
   // one buffer, two lives: record staging while loading, then the signed digits [digit][thread] (conflict-free columns)
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(i
   uint4(*stage)[256] = reinterpret_cast<uint4(*)[256]>(smem_raw);
   int32_t *digits = reinterpret_cast<int32_t *>(smem_raw) + threadIdx.x;
   const size_t n = n_ptr ? (size_t)*n_ptr : n_arg;
-  for (size_t base = (size_t)blockIdx.x * HS_THREADS; base < n; base += (size_t)gridDim.x * HS_THREADS) {
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += (size_t)gridDim.x * blockDim.x) {  // blockDim <= HS_THREADS
   const size_t t = base + threadIdx.x;
   const size_t warp_first = t & ~(size_t)31;
   // (no early exit for warps past the end: every warp of the block reaches the barriers below; they clamp and do not store)
@@ -198,8 +202,8 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? 4 : 3) k_verify_main(i
     meta = verify_committee_main(acc, R, S, h, btable, C.atables + (size_t)v * C.table_entries, have_key ? C.key_flags[v] : 0u, digits,
                                  HS_THREADS, cp);
     if (!have_key) {
-      meta = HS_META_MISS;
-      if (active && O.miss_list) O.miss_list[atomicAdd(O.miss_count, 1u)] = (uint32_t)i;
+      if (O.side_pass) continue;  // unknown key bytes: the generic pass on the side stream owns this record's outputs
+      meta = 0;                   // unknown authority INDEX: reject (messages.rs:57-61 rejects it before any crypto)
     }
   } else {
     ge_cached tab[9];
@@ -332,8 +336,8 @@ struct dev_buf {
 };
 struct hs_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_side = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_side[2] = {nullptr, nullptr};
   ge_niels *d_btable = nullptr;
   comb_params cp{};
   size_t a_table_entries = 0;
@@ -405,7 +409,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   if (n == 0) return HS_OK;
   HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
   HS_TRY(ensure(c, c->meta, n));
-  main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, nullptr, nullptr};
+  main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, 0};
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
   if (indexed && c->n_keys == 0) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
@@ -414,24 +418,28 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
       HS_TRY(ensure(c, c->vidx, n * 4));
       HS_TRY(ensure(c, c->miss, n * 4));
       key_table T{c->d_slots, c->slot_mask, c->d_pks, (uint32_t)c->n_keys};
-      k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)c->vidx.p);
-      c->launches++;
-      L.vidx = (const uint32_t *)c->vidx.p;
-      O.miss_list = (uint32_t *)c->miss.p;
-      O.miss_count = c->d_miss_count;
       HS_CUDA(c, cudaMemsetAsync(c->d_miss_count, 0, 4, stream));
+      k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)c->vidx.p, (uint32_t *)c->miss.p, c->d_miss_count);
+      c->launches++;
+      HS_CUDA(c, cudaGetLastError());
+      L.vidx = (const uint32_t *)c->vidx.p;
+      O.side_pass = 1;
+      // Records whose key is not registered take the generic path over the compacted list.  One generic verify has a
+      // ~0.8 ms single-warp latency, so the pass runs on the high-priority side stream CONCURRENTLY with the committee
+      // pass (disjoint outputs); its length stays on the device (no host round trip).
+      HS_CUDA(c, cudaEventRecord(c->ev_side[0], stream));
+      HS_CUDA(c, cudaStreamWaitEvent(c->stream_side, c->ev_side[0], 0));
+      unsigned grid = blocks_for(n, 32);
+      if (grid > 148u * 8u) grid = 148u * 8u;
+      k_verify_main<false><<<grid, 32, 0, c->stream_side>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O, c->cp);
+      c->launches++;
+      HS_CUDA(c, cudaGetLastError());
+      HS_CUDA(c, cudaEventRecord(c->ev_side[1], c->stream_side));
     }
     k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
-    if (!indexed) {
-      // records whose key is not registered: generic path over the compacted list; the count stays on the device
-      unsigned grid = blocks_for(n);
-      if (grid > 148u * 4u) grid = 148u * 4u;
-      k_verify_main<false><<<grid, HS_THREADS, 0, stream>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O, c->cp);
-      c->launches++;
-      HS_CUDA(c, cudaGetLastError());
-    }
+    if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_side[1], 0));
   } else {
     k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
@@ -475,9 +483,15 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&c->stream_side, cudaStreamNonBlocking, hi);
+  }
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_side[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
   if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
@@ -513,7 +527,9 @@ void hs_ctx_destroy(hs_ctx *c) {
   for (int i = 0; i < 2; i++) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]);
   }
+  if (c->stream_side) cudaStreamDestroy(c->stream_side);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
@@ -568,13 +584,13 @@ int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out
   HS_CUDA(c, cudaMalloc(&c->d_pks, N * 32));
   HS_CUDA(c, cudaMalloc(&c->d_key_flags, N));
   HS_CUDA(c, cudaMalloc(&c->d_slots, (size_t)cap * 4));
-  // widest per-key window whose tables fit in ~45 % of the device (B200: 16 bits up to ~1.6 k keys, 14 up to ~5 k, 12 up to ~19 k)
+  // widest per-key window whose tables fit in ~62 % of the device (B200: 16 bits up to ~2.2 k keys, 15 up to ~4.2 k, 14 up to ~7.6 k, 12 up to ~26 k)
   size_t free_b = 0, total_b = 0;
   HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = total_b / 100 * 45;
+  size_t budget = total_b / 100 * 62;
   if (budget > free_b - free_b / 8) budget = free_b - free_b / 8;
   int wa = 8;
-  for (int w : {16, 14, 12, 10, 8}) {
+  for (int w : {16, 15, 14, 13, 12, 11, 10, 9, 8}) {
     if (c->wa_forced && w != c->wa_forced) continue;
     wa = w;
     if (N * comb_table_entries(w) * sizeof(ge_niels) <= budget) break;

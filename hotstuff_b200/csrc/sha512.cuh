@@ -14,6 +14,7 @@
 
 #if defined(__CUDACC__)
 __device__ __constant__ uint64_t HS_SHA512_K_DEV[80] = {HS_SHA512_K_INIT};
+__device__ __constant__ uint32_t HS_ONE_DEV = 1;  // opaque multiplier: keeps ptxas from folding mad.wide(x, 1, y) back into ALU adds
 #endif
 
 HS_HD uint64_t sha_k(int i) {
@@ -25,6 +26,19 @@ HS_HD uint64_t sha_k(int i) {
 }
 
 HS_HD uint64_t rotr64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+// SHA-512 on a 32-bit datapath is ALU-pipe bound (rotates, xors and add/add-with-carry all issue there: ncu shows the
+// digest kernel at 86 % ALU-pipe utilisation).  Experiment HS_SHA_FMA_ADD moves half of every 64-bit add to the FMA pipe
+// (x + y = mad.wide(x_lo, 1, y) + (x_hi << 32)); measured on B200 it is SLOWER (1.95 ms vs 1.33 ms per 2^20 x 512 B:
+// IMAD.WIDE costs ~2.4 issue cycles and drags register moves along), so the plain adds stay the default.
+HS_HD uint64_t add64_fma(uint64_t x, uint64_t y) {
+#if defined(__CUDA_ARCH__) && defined(HS_SHA_FMA_ADD)
+  uint64_t t;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"((uint32_t)x), "r"(HS_ONE_DEV), "l"(y));
+  return t + (x & 0xffffffff00000000ULL);
+#else
+  return x + y;
+#endif
+}
 HS_HD uint32_t bswap32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
   return __byte_perm(x, 0, 0x0123);
@@ -51,16 +65,16 @@ HS_HD void sha512_init(sha512_state &s) {
 // stall cycles of the digest kernel were "no instruction").
 #define HS_SHA_ROUND(a, b, c, d, e, f, g, h, kw)                                 \
   {                                                                              \
-    uint64_t t1_ = h + (rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)) + ((e & f) ^ (~e & g)) + (kw); \
-    uint64_t t2_ = (rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39)) + ((a & b) ^ (a & c) ^ (b & c));   \
-    d += t1_;                                                                    \
-    h = t1_ + t2_;                                                               \
+    uint64_t t1_ = add64_fma(add64_fma(h, rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41)), add64_fma((e & f) ^ (~e & g), (kw))); \
+    uint64_t t2_ = add64_fma(rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39), (a & b) ^ (a & c) ^ (b & c));   \
+    d = add64_fma(d, t1_);                                                       \
+    h = add64_fma(t1_, t2_);                                                     \
   }
 #define HS_SHA_SCHED(w, j)                                                                          \
   {                                                                                                 \
     uint64_t w15_ = w[((j) + 1) & 15], w2_ = w[((j) + 14) & 15];                                    \
-    w[(j) & 15] += (rotr64(w15_, 1) ^ rotr64(w15_, 8) ^ (w15_ >> 7)) + w[((j) + 9) & 15] +          \
-                   (rotr64(w2_, 19) ^ rotr64(w2_, 61) ^ (w2_ >> 6));                               \
+    w[(j) & 15] = add64_fma(add64_fma(w[(j) & 15], rotr64(w15_, 1) ^ rotr64(w15_, 8) ^ (w15_ >> 7)),  \
+                            add64_fma(w[((j) + 9) & 15], rotr64(w2_, 19) ^ rotr64(w2_, 61) ^ (w2_ >> 6))); \
   }
 #define HS_SHA_8ROUNDS(w, base, j0)                                   \
   HS_SHA_ROUND(a, b, c, d, e, f, g, h, sha_k((base) + (j0) + 0) + w[(j0) + 0]) \

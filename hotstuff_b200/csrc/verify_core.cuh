@@ -108,9 +108,28 @@ HS_HD void ge_comb_accumulate_rt(ge_ext &acc, const ge_niels *table, const int32
 // acc = sum over the A windows of digit * 2^(wa i) * (-A)  +  sum over the B windows of digit * 2^(wb i) * B.
 // dig[0 .. na) are k's digits, dig[na .. na+nb) are S's.  ONE loop body (one copy of the mixed addition in the
 // instruction cache) with the table entry of iteration i+1 fetched while iteration i's addition executes.
+#ifndef HS_PREFETCH
+#define HS_PREFETCH 1
+#endif
 HS_HD void ge_comb_ab(ge_ext &acc, const ge_niels *atab, const ge_niels *btab, const int32_t *dig, int stride, const comb_params &cp) {
   const int NA = cp.na, NT = cp.na + cp.nb;
   ge_identity(acc);
+#if !HS_PREFETCH
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int j = 0; j < NT; j++) {
+    int d = dig[j * stride];
+    uint32_t neg = (uint32_t)(d < 0);
+    int mag = d < 0 ? -d : d;
+    ge_niels q;
+    if (mag == 0) ge_niels_identity(q);
+    else if (j < NA) niels_load_stream(q, atab + ((size_t)j << (cp.wa - 1)) + (mag - 1));
+    else niels_load(q, btab + ((size_t)(j - NA) << (cp.wb - 1)) + (mag - 1));
+    ge_madd_signed(acc, acc, q, neg);
+  }
+  return;
+#endif
   ge_niels qn;
   uint32_t negn;
   {

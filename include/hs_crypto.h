@@ -52,7 +52,7 @@ typedef struct {
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
 /* device: CUDA ordinal.  Builds the base-point comb table on the GPU (default window 24 bits = 8.9 GB of HBM).
  * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..24), bits 8-15 = forced per-key window width
- * (8/10/12/14/16; 0 = widest that fits ~45 % of device memory). */
+ * (8..16; 0 = widest that fits ~62 % of device memory). */
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
