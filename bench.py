@@ -373,6 +373,23 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = ALGO_BYTES_VERIFY * n / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        try:  # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = tr.get("k_verify_main_bytes_per_record", 0) * n or None
+        except Exception:
+            pass
+        wa, wb = eng.window_bits
+
+        def ndig(w):
+            r = 253 % w
+            return (253 + w - 1) // w + (1 if r in (0, w - 1) else 0)
+        adds = (ndig(wa) if wa else 64) + ndig(wb)
+        # wide multiplies (IMAD.WIDE.U32[.X]) per verify: 7 field multiplications x 71 per mixed addition (SASS count of the hot
+        # loop), + ~0.7 k for the mod-l reduction and the batched-inversion share; generic keys add 252 doublings + decompression
+        wide_per_verify = adds * 7 * 71 + 700 + (0 if wa else 252 * 7 * 56 + 20000)
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        wide_rate = wide_per_verify * n / (kern_ms * 1e-3) / (148 * sm_clk * 1e6)
         line = {
             "metric": "Ed25519 verifies/s", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
@@ -380,10 +397,14 @@ def main():
             "e2e": e2e,
             "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s", "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s", "traffic": traffic,
                          "kernel_ms": kern_ms, "kernel_ms_covers": "lookup + main + finish kernels of one verify pass over 2^20 resident records",
                          "algorithmic_bytes_per_verify": ALGO_BYTES_VERIFY,
                          "note": "integer-ALU bound path: 128 B of compulsory I/O per ~0.1-0.3 M INT32 instructions; HBM fraction is necessarily << 1 (SURVEY §0.7)"},
+            "alu_roofline": {"bound": "IMAD.WIDE issue (FMA-heavy pipe) — the resource that actually binds this path", "unit": "wide-mads/clk/SM",
+                             "achieved": wide_rate, "peak": 54.0, "frac": wide_rate / 54.0, "wide_mads_per_verify": wide_per_verify,
+                             "mixed_additions_per_verify": adds, "window_bits": {"key": wa, "base": wb},
+                             "peak_source": "tools/microbench/pipes.cu on B200 (profiles/r01_pipes.txt); ncu sm__pipe_fmaheavy_cycles_active for this kernel: profiles/r01_ncu_summary.md"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -62,6 +62,13 @@ class Engine:
             raise EngineError("%s failed: status %d: %s" % (what, rc, self.lib.hs_last_error(self.h).decode()))
 
     @property
+    def window_bits(self):
+        """(per-key comb window bits or 0, base-point comb window bits)"""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self.lib.hs_window_bits(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    @property
     def kernel_launches(self):
         return int(self.lib.hs_kernel_launches(self.h))
 

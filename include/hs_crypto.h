@@ -57,6 +57,8 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
 const char *hs_last_error(const hs_ctx *ctx);
+/* Comb window widths in use: per-key tables (0 when no committee is registered) and the base-point table. */
+void hs_window_bits(const hs_ctx *ctx, int *key_bits, int *base_bits);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t hs_kernel_launches(const hs_ctx *ctx);
 /* Pinned host memory helpers (optional; any host pointer is accepted by the host entry points). */
