@@ -191,6 +191,39 @@ def gen_reduce(pr, c, out):
     gen_fold_top(pr, c, "t8", "red")
 
 
+def gen_reduce_split(pr, E, O, out):
+    """Fold a 512-bit value held as TWO interleaved accumulator arrays — E[k] at column k (k = 0..15, even-aligned pairs)
+    and O[k] at column k+1 (k = 0..14, odd-aligned pairs) — down to out[0..7] without ever re-pairing a register:
+    high limbs at even columns fold (x38) into E's low pairs, high limbs at odd columns into O's low pairs, so every
+    wide multiply-accumulate keeps the (even, odd) register pair it was born with (no IMAD.MOV shuffles in SASS)."""
+    assert [E % k for k in range(8)] == list(out)
+    h = {}
+    for p in range(8, 16):
+        h[p] = "h%d" % p
+        op = "add.cc.u32" if p == 8 else ("addc.cc.u32" if p < 15 else "addc.u32")
+        pr.emit(op, h[p], E % p, O % (p - 1))
+    first = True
+    for j in (0, 2, 4, 6):                                  # even columns -> E pairs (j, j+1)
+        pr.emit("mad.lo.cc.u32" if first else "madc.lo.cc.u32", E % j, h[8 + j], 38, E % j)
+        pr.emit("madc.hi.cc.u32", E % (j + 1), h[8 + j], 38, E % (j + 1))
+        first = False
+    pr.emit("addc.u32", "te", 0, 0)                          # column 8
+    first = True
+    for j in (1, 3, 5, 7):                                  # odd columns -> O pairs (columns j, j+1) = O[j-1], O[j]
+        lo, hi = O % (j - 1), (O % j) if j < 7 else "x7"
+        pr.emit("mad.lo.cc.u32" if first else "madc.lo.cc.u32", lo, h[8 + j], 38, lo)
+        if j < 7:
+            pr.emit("madc.hi.cc.u32", hi, h[8 + j], 38, hi)
+        else:
+            pr.emit("madc.hi.u32", hi, h[8 + j], 38, 0)     # column 8, fresh (O[7] was consumed by h8)
+        first = False
+    pr.emit("add.cc.u32", out[1], E % 1, O % 0)
+    for k in range(2, 8):
+        pr.emit("addc.cc.u32", out[k], E % k, O % (k - 1))
+    pr.emit("addc.u32", "t8", "te", "x7")
+    gen_fold_top(pr, list(out), "t8", "red")
+
+
 def gen_mul():
     pr = Prog()
     a = ["a%d" % i for i in range(8)]
@@ -214,16 +247,14 @@ def gen_mul():
         chain_row(pr, E, de, a[i], te, 16)
         chain_row(pr, O, do, a[i], to, 15)
     assert de == set(range(16)) and do == set(range(15)), (de, do)
-    # merge: c[k] = e[k] + o[k-1]
-    pr.emit("add.cc.u32", E % 1, E % 1, "o0")
-    for k in range(2, 15):
-        pr.emit("addc.cc.u32", E % k, E % k, O % (k - 1))
-    pr.emit("addc.u32", "e15", "e15", "o14")
-    gen_reduce(pr, [E % k for k in range(16)], ["r%d" % k for k in range(8)])
+    class ONames:
+        def __mod__(self, k):
+            return "o%d" % k
+    gen_reduce_split(pr, E, ONames(), ["r%d" % k for k in range(8)])
     return pr
 
 
-def gen_sqr():
+def gen_sqr(split=True):
     pr = Prog()
     a = ["a%d" % i for i in range(8)]
     E, O = "e%d", "o%d"
@@ -240,36 +271,58 @@ def gen_sqr():
                     dset |= {lo, lo + 1}
             else:
                 chain_row(pr, arr, dset, a[i], terms, lim)
-    # off-diagonal sum S occupies columns 1..14 (< 2^511); e covers even-aligned pairs, o odd-aligned
-    lo_e, hi_e = min(de), max(de)
-    lo_o, hi_o = min(do), max(do)
-    # c[k] = e[k] + o[k-1] for k in 0..15 (missing -> 0)
-    c = []
-    first = True
-    for k in range(16):
-        ek = (E % k) if k in de else None
-        ok = (O % (k - 1)) if (k - 1) in do else None
-        name = ("r%d" % k) if k < 8 else ("c%d" % k)
-        if ek is None and ok is None:
-            pr.emit("add.u32", name, 0, 0) if first else pr.emit("addc.cc.u32", name, 0, 0)
-        elif first:
-            # no carry can exist yet
-            if ek is not None and ok is not None:
-                pr.emit("add.cc.u32", name, ek, ok); first = False
+    if not split:
+        # off-diagonal sum S occupies columns 1..14 (< 2^511); e covers even-aligned pairs, o odd-aligned
+        # c[k] = e[k] + o[k-1] for k in 0..15 (missing -> 0)
+        c = []
+        first = True
+        for k in range(16):
+            ek = (E % k) if k in de else None
+            ok = (O % (k - 1)) if (k - 1) in do else None
+            name = ("r%d" % k) if k < 8 else ("c%d" % k)
+            if ek is None and ok is None:
+                pr.emit("add.u32", name, 0, 0) if first else pr.emit("addc.cc.u32", name, 0, 0)
+            elif first:
+                if ek is not None and ok is not None:
+                    pr.emit("add.cc.u32", name, ek, ok); first = False
+                else:
+                    pr.emit("add.u32", name, ek if ek is not None else ok, 0)
             else:
-                pr.emit("add.u32", name, ek if ek is not None else ok, 0)
-        else:
-            pr.emit("addc.cc.u32", name, ek if ek is not None else 0, ok if ok is not None else 0)
-        c.append(name)
-    # double: c = 2*S
-    for k in range(15, 0, -1):
-        pr.emit("shf.l", c[k], c[k - 1], c[k], 1)
-    pr.emit("shf.l", c[0], 0, c[0], 1)
-    # add the diagonal a_i^2 at column 2i
+                pr.emit("addc.cc.u32", name, ek if ek is not None else 0, ok if ok is not None else 0)
+            c.append(name)
+        for k in range(15, 0, -1):
+            pr.emit("shf.l", c[k], c[k - 1], c[k], 1)
+        pr.emit("shf.l", c[0], 0, c[0], 1)
+        for i in range(8):
+            pr.emit("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", c[2 * i], a[i], a[i], c[2 * i])
+            pr.emit("madc.hi.cc.u32", c[2 * i + 1], a[i], a[i], c[2 * i + 1])
+        gen_reduce(pr, c, ["r%d" % k for k in range(8)])
+        return pr
+    # off-diagonal sum S = E + (O << 32) occupies columns 1..14 (< 2^511).  2S = 2E + (2O << 32): double each array on its
+    # own (the arrays never merge, so no register changes its pair), then add the diagonal a_i^2 at column 2i into E's pairs.
+    class EN:
+        def __mod__(self, k):
+            return ("r%d" % k) if k < 8 else ("f%d" % k)
+    class ON:
+        def __mod__(self, k):
+            return "g%d" % k
+    NE, NO = EN(), ON()
+    for arr, dset, new, n in ((E, de, NE, 16), (O, do, NO, 15)):
+        for k in range(n - 1, -1, -1):
+            cur = (arr % k) if k in dset else None
+            prev = (arr % (k - 1)) if (k - 1) in dset else None
+            if cur is None and prev is None:
+                pr.emit("add.u32", new % k, 0, 0)
+            elif prev is None:
+                pr.emit("add.u32", new % k, cur, cur)            # low limb of a run: plain shift left by one
+            elif cur is None:
+                pr.emit("shf.l", new % k, prev, 0, 1)            # only the bit shifted out of the limb below
+            else:
+                pr.emit("shf.l", new % k, prev, cur, 1)
     for i in range(8):
-        pr.emit("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", c[2 * i], a[i], a[i], c[2 * i])
-        pr.emit("madc.hi.cc.u32", c[2 * i + 1], a[i], a[i], c[2 * i + 1])
-    gen_reduce(pr, c, ["r%d" % k for k in range(8)])
+        pr.emit("mad.lo.cc.u32" if i == 0 else "madc.lo.cc.u32", NE % (2 * i), a[i], a[i], NE % (2 * i))
+        pr.emit("madc.hi.cc.u32" if i < 7 else "madc.hi.u32", NE % (2 * i + 1), a[i], a[i], NE % (2 * i + 1))
+    gen_reduce_split(pr, NE, NO, ["r%d" % k for k in range(8)])
     return pr
 
 
@@ -326,11 +379,46 @@ def check_addsub(pr, is_sub):
     assert trace, "rare path never exercised"
 
 
+def check_reduce_split():
+    """gen_reduce_split on arbitrary (E, O) pairs with E + (O << 32) < 2^512, including rare-ripple inputs."""
+    class EN:
+        def __mod__(self, k):
+            return ("r%d" % k) if k < 8 else ("e%d" % k)
+    class ON:
+        def __mod__(self, k):
+            return "o%d" % k
+    pr = Prog()
+    gen_reduce_split(pr, EN(), ON(), ["r%d" % k for k in range(8)])
+    rnd = random.Random(11)
+    trace = set()
+    cases = []
+    for _ in range(4000):
+        v = rnd.getrandbits(512) if rnd.random() < 0.7 else (1 << 512) - 1 - rnd.getrandbits(rnd.randrange(1, 200))
+        o = rnd.getrandbits(480) if rnd.random() < 0.8 else (1 << 480) - 1
+        o = min(o, v >> 32)
+        cases.append((v - (o << 32), o))
+    for _ in range(3000):   # engineered: result just below 2^256 before the last fold
+        hi = rnd.getrandbits(256)
+        lo = (((1 << 256) - rnd.randrange(1, 3000)) - 38 * hi) % (1 << 256)
+        v = (hi << 256) | lo
+        o = rnd.getrandbits(480)
+        o = min(o, v >> 32)
+        cases.append((v - (o << 32), o))
+    for e, o in cases:
+        env = {EN() % k: (e >> (32 * k)) & M32 for k in range(16)}
+        env.update({"o%d" % k: (o >> (32 * k)) & M32 for k in range(15)})
+        out = pr.run(env, trace)
+        r = sum(out["r%d" % i] << (32 * i) for i in range(8))
+        assert r < (1 << 256) and r % P == (e + (o << 32)) % P, (hex(e), hex(o))
+    assert "L_red" in trace, "split-reduce ripple never exercised"
+
+
 def check_reduce():
     """gen_reduce on arbitrary 512-bit inputs, including ones built to hit the out-of-line ripple."""
     pr = Prog()
     c = ["r%d" % k for k in range(8)] + ["e%d" % k for k in range(8, 16)]
     gen_reduce(pr, c, c[:8])
+    check_reduce_split()
     rnd = random.Random(7)
     trace = set()
     cases = [rnd.getrandbits(512) for _ in range(3000)] + [(1 << 512) - 1, 0, (1 << 256) - 1, ((1 << 256) - 1) << 256]
@@ -404,7 +492,7 @@ def count(pr):
 
 
 if __name__ == "__main__":
-    m, s = gen_mul(), gen_sqr()
+    m, s = gen_mul(), gen_sqr(split=os.environ.get('HS_SQR_SPLIT', '0') == '1')
     check(m, False)
     check(s, True)
     check_reduce()
