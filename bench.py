@@ -204,6 +204,120 @@ def workload_config(args, world):
             "parallelism": "records sharded across %d rank(s); all-gather of accept bitmaps" % world}
 
 
+# ------------------------------------------------------------------------------------------------ QC workload (configs 2/3)
+def make_qc_inputs(n_val, n_qc, votes_per_qc, seed):
+    """Committee of n_val validators; n_qc QCs, each with votes_per_qc distinct signers over QC::digest =
+    SHA-512(hash || round_le)[..32] (consensus/src/messages.rs:201-208).  1 % of the votes get one flipped signature bit."""
+    from concurrent.futures import ProcessPoolExecutor
+    from cryptography.hazmat.primitives import serialization
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    import hashlib
+    rng = np.random.default_rng(seed)
+    seeds = rng.integers(0, 256, size=(n_val, 32), dtype=np.uint8)
+    pks = np.zeros((n_val, 32), dtype=np.uint8)
+    for k in range(n_val):
+        pks[k] = np.frombuffer(Ed25519PrivateKey.from_private_bytes(seeds[k].tobytes()).public_key().public_bytes(
+            serialization.Encoding.Raw, serialization.PublicFormat.Raw), dtype=np.uint8)
+    pre = np.zeros((n_qc, 40), dtype=np.uint8)
+    pre[:, :32] = rng.integers(0, 256, size=(n_qc, 32), dtype=np.uint8)
+    pre[:, 32:] = np.arange(1, n_qc + 1, dtype="<u8").view(np.uint8).reshape(n_qc, 8)
+    digests = np.array([np.frombuffer(hashlib.sha512(pre[j].tobytes()).digest()[:32], dtype=np.uint8) for j in range(n_qc)])
+    n = n_qc * votes_per_qc
+    vidx = np.concatenate([rng.choice(n_val, size=votes_per_qc, replace=False) for _ in range(n_qc)]).astype(np.uint32)
+    midx = np.repeat(np.arange(n_qc, dtype=np.uint32), votes_per_qc)
+    nproc = max(1, min(64, host_cores()))
+    chunks = np.array_split(np.arange(n), nproc * 4)
+    with ProcessPoolExecutor(max_workers=nproc) as ex:
+        parts = list(ex.map(_sign_chunk, [(seeds, vidx[c], digests[midx[c]]) for c in chunks if len(c)]))
+    sig = np.concatenate(parts, axis=0)
+    bad = rng.choice(n, size=n // 100, replace=False)
+    sig[bad, rng.integers(0, 64, bad.shape[0])] ^= (1 << rng.integers(0, 8, bad.shape[0])).astype(np.uint8)
+    corrupted = np.zeros(n, dtype=bool)
+    corrupted[bad] = True
+    return dict(pks=pks, pre=pre, digests=digests, vidx=vidx, midx=midx, sig=sig, corrupted=corrupted)
+
+
+def run_qc(args):
+    import torch
+    import torch.distributed as dist
+    from hotstuff_b200 import Engine, build
+    from hotstuff_b200.sharding import shard_range, all_gather_bitmap
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    build.build_engine()
+    eng = Engine(local_rank)
+    inp = make_qc_inputs(args.committee, args.qcs, args.votes_per_qc, seed=4321)   # identical on every rank (seeded)
+    n = inp["sig"].shape[0]
+    lo, hi, per = shard_range(n, rank, world)
+    assert eng.committee_register(inp["pks"]).all()
+    d_pre = torch.from_numpy(inp["pre"].reshape(-1)).to(dev)
+    d_off = torch.arange(args.qcs + 1, dtype=torch.int64, device=dev) * 40
+    d_dig = torch.empty((args.qcs, 32), dtype=torch.uint8, device=dev)
+    d_sig = torch.from_numpy(inp["sig"][lo:hi]).to(dev)
+    d_vidx = torch.from_numpy(inp["vidx"][lo:hi].astype(np.int32)).to(dev)
+    d_midx = torch.from_numpy(inp["midx"][lo:hi].astype(np.int32)).to(dev)
+    d_midx_all = torch.from_numpy(inp["midx"].astype(np.int64)).to(dev)
+    words_local = (hi - lo + 31) // 32
+    d_bm = torch.zeros(max(1, words_local), dtype=torch.int32, device=dev)
+    d_idx = torch.arange(n, dtype=torch.int64, device=dev)
+
+    def step():
+        eng.digest32_dev(d_pre, d_off, d_dig, args.qcs)                                    # QC::digest for every certificate
+        eng.verify_committee_dev(d_vidx, d_sig, d_dig, d_bm, hi - lo, d_midx=d_midx, mode=1)  # verify_batch condition per vote
+        full = all_gather_bitmap(d_bm[:words_local], n, world)                              # every rank gets every verdict
+        bits = (full[d_idx >> 5] >> (d_idx & 31)) & 1
+        qc_ok = torch.ones(args.qcs, dtype=torch.int32, device=dev).scatter_reduce(0, d_midx_all, bits.to(torch.int32), reduce="amin")
+        return full, qc_ok
+
+    for _ in range(max(3, args.warmup)):
+        full, qc_ok = step()
+    torch.cuda.synchronize()
+    bits = np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+    assert (bits == ~inp["corrupted"]).all(), "vote verdicts differ from the expected pattern"
+    want_qc = np.ones(args.qcs, dtype=bool)
+    np.logical_and.at(want_qc, inp["midx"], ~inp["corrupted"])
+    assert (qc_ok.cpu().numpy().astype(bool) == want_qc).all(), "per-QC AND differs"
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        wa, wb = eng.window_bits
+        print(json.dumps({
+            "metric": "Ed25519 verifies/s", "value": n * args.steps / (ms * 1e-3), "unit": "verifies/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "gpu_launches": int(eng.kernel_launches - l0), "clocks": clocks,
+            "config": {"workload": "QC verification: committee=%d, %d QCs x %d votes = %d votes (BASELINE config[%d]); QC::digest on GPU, "
+                                   "verify_batch condition per vote, all-gather of accept bitmaps, per-QC AND" % (
+                                       args.committee, args.qcs, args.votes_per_qc, n, 2 if args.committee <= 1000 else 3),
+                       "votes": n, "shard": "contiguous ranges of %d votes per rank" % per, "window_bits": {"key": wa, "base": wb},
+                       "l2": "per-key tables (%d keys) far larger than L2; inputs %.0f MB" % (args.committee, n * 72 / 1e6)}}))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -222,10 +336,19 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-pointer leg")
+    ap.add_argument("--workload", default="msgs", choices=["msgs", "qc"],
+                    help="msgs: BASELINE config[1] (default, the driver's headline).  qc: BASELINE config[2]/[3] — a committee of --committee "
+                         "validators, --qcs quorum certificates of --votes-per-qc votes each, verify_batch semantics per vote + per-QC AND; "
+                         "with --gpus N the votes are sharded across ranks (strong scaling) and the bitmaps all-gathered")
+    ap.add_argument("--committee", type=int, default=1000)
+    ap.add_argument("--qcs", type=int, default=10000)
+    ap.add_argument("--votes-per-qc", type=int, default=100)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "qc":
+        return run_qc(args)
 
     import torch
     import torch.distributed as dist
