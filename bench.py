@@ -24,6 +24,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries exactly one JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
@@ -198,7 +201,8 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "config[1]: 2^20 signatures per GPU, 512 B msgs: Digest(msg)=SHA-512[..32] on GPU then verify_strict over the digest",
+    coll = "none (1 rank)" if world == 1 else ("fused peer-store all-gather in the finish kernel (NVLink P2P)" if args.collective == "peer" else "ncclAllGather")
+    return {"collective": coll,"workload": "config[1]: 2^20 signatures per GPU, 512 B msgs: Digest(msg)=SHA-512[..32] on GPU then verify_strict over the digest",
             "records_per_gpu": args.n, "msg_len": args.msg_len, "distinct_keys": args.keys, "corrupted_frac": 0.01,
             "key_mode": args.key_mode, "l2": "inputs (%.0f MB/GPU) larger than the 126 MB L2" % (args.n * (96 + args.msg_len) / 1e6),
             "parallelism": "records sharded across %d rank(s); all-gather of accept bitmaps" % world}
@@ -265,11 +269,17 @@ def run_qc(args):
     words_local = (hi - lo + 31) // 32
     d_bm = torch.zeros(max(1, words_local), dtype=torch.int32, device=dev)
     d_idx = torch.arange(n, dtype=torch.int64, device=dev)
+    pag = None
+    if world > 1 and args.collective == "peer":
+        from hotstuff_b200.sharding import PeerAllGather
+        pag = PeerAllGather(eng, n, rank, world)
 
     def step():
         eng.digest32_dev(d_pre, d_off, d_dig, args.qcs)                                    # QC::digest for every certificate
+        if pag is not None:
+            pag.arm()
         eng.verify_committee_dev(d_vidx, d_sig, d_dig, d_bm, hi - lo, d_midx=d_midx, mode=1)  # verify_batch condition per vote
-        full = all_gather_bitmap(d_bm[:words_local], n, world)                              # every rank gets every verdict
+        full = pag.bitmap() if pag is not None else all_gather_bitmap(d_bm[:words_local], n, world)  # every rank gets every verdict
         bits = (full[d_idx >> 5] >> (d_idx & 31)) & 1
         qc_ok = torch.ones(args.qcs, dtype=torch.int32, device=dev).scatter_reduce(0, d_midx_all, bits.to(torch.int32), reduce="amin")
         return full, qc_ok
@@ -312,6 +322,7 @@ def run_qc(args):
                                    "verify_batch condition per vote, all-gather of accept bitmaps, per-QC AND" % (
                                        args.committee, args.qcs, args.votes_per_qc, n, 2 if args.committee <= 1000 else 3),
                        "votes": n, "shard": "contiguous ranges of %d votes per rank" % per, "window_bits": {"key": wa, "base": wb},
+                       "collective": "none (1 rank)" if world == 1 else ("fused peer-store all-gather (NVLink P2P)" if pag is not None else "ncclAllGather"),
                        "l2": "per-key tables (%d keys) far larger than L2; inputs %.0f MB" % (args.committee, n * 72 / 1e6)}}))
     if world > 1:
         dist.destroy_process_group()
@@ -340,6 +351,9 @@ def main():
                     help="msgs: BASELINE config[1] (default, the driver's headline).  qc: BASELINE config[2]/[3] — a committee of --committee "
                          "validators, --qcs quorum certificates of --votes-per-qc votes each, verify_batch semantics per vote + per-QC AND; "
                          "with --gpus N the votes are sharded across ranks (strong scaling) and the bitmaps all-gathered")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the per-rank accept bitmaps reach every rank.  peer: the verify finish kernel stores its words straight "
+                         "into every rank's buffer over NVLink (fused all-gather, hs_peer_*).  nccl: ncclAllGather after the kernel (baseline)")
     ap.add_argument("--committee", type=int, default=1000)
     ap.add_argument("--qcs", type=int, default=10000)
     ap.add_argument("--votes-per-qc", type=int, default=100)
@@ -381,9 +395,16 @@ def main():
         assert eng.committee_register(inp["pks"]).all()
     indexed = args.key_mode == "indexed"
 
+    pag = None
+    if world > 1 and args.collective == "peer":
+        from hotstuff_b200.sharding import PeerAllGather
+        pag = PeerAllGather(eng, n * world, rank, world)
+
     def step_resident():
+        if pag is not None:
+            pag.arm()   # the finish kernel of the next call writes this rank's words into every rank's buffer + signals
         eng.verify_msgs_dev(d_sig, d_msgs, L, d_digest, d_bitmap, n, d_pk=None if indexed else d_pk, d_vidx=d_vidx if indexed else None)
-        if world > 1:
+        if world > 1 and pag is None:
             dist.all_gather_into_tensor(d_all, d_bitmap)
 
     def expected_bits():
@@ -400,7 +421,18 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
-    check(d_bitmap.cpu().numpy())
+    if world > 1:
+        # every rank must hold every rank's verdicts: check this rank's slice of the gathered bitmap, and that the other
+        # slices are populated (each rank's inputs differ only by seed, ~1 % rejected everywhere)
+        full = (pag.full if pag is not None else d_all).cpu().numpy()
+        check(full[rank * words:(rank + 1) * words].copy())
+        for r in range(world):
+            ones = int(np.unpackbits(full[r * words:(r + 1) * words].view(np.uint8)).sum())
+            assert 0.98 * n < ones < n, "rank %d sees no plausible bitmap from rank %d" % (rank, r)
+        if pag is not None:
+            assert not eng.lib.hs_peer_timed_out(eng.h), "peer wait timed out"
+    else:
+        check(d_bitmap.cpu().numpy())
 
     d_arange = torch.arange(n, dtype=torch.int32, device=dev)
     d_recs = torch.empty((n, 128), dtype=torch.uint8, device=dev)

@@ -227,6 +227,35 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU epilogue
+// The accept bitmap of a sharded verify has to reach every rank (each validator process needs every verdict).  Instead of a
+// separate all-gather collective after the kernel, the finish kernel stores each bitmap word it produces straight into EVERY
+// peer's result buffer over NVLink (P2P stores through CUDA-IPC mapped pointers), then a release flag per (writer, reader)
+// pair tells the reader the shard has landed.  Payload is n/8 bytes per rank: latency, not bandwidth.
+#define HS_MAX_PEERS 16
+struct peer_route {
+  uint32_t *buf[HS_MAX_PEERS];  // buf[p] = base of rank p's result buffer as mapped in THIS process (words, then flags)
+  int n;                        // world size (0 = route disabled: plain local bitmap)
+  size_t word_offset;           // this rank's first word in the global bitmap
+};
+__global__ void k_peer_signal(peer_route P, size_t total_words, int my_rank, uint32_t epoch) {
+  const int p = threadIdx.x;
+  if (p >= P.n) return;
+  __threadfence_system();  // the finish kernel's peer stores (previous launch on this stream) are ordered before the flag
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.buf[p] + total_words + my_rank), "r"(epoch) : "memory");
+}
+__global__ void k_peer_wait(const uint32_t *flags, int n, uint32_t epoch, uint32_t *timeout_flag) {
+  const int p = threadIdx.x;
+  if (p >= n) return;
+  uint32_t v = 0;
+  for (long long spin = 0; spin < (1ll << 27); spin++) {  // bounded: a missing peer becomes an error, never a hang
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+    if ((int32_t)(v - epoch) >= 0) return;
+    __nanosleep(200);
+  }
+  *timeout_flag = 1;
+}
+
 // ------------------------------------------------------------------------------------------------ phase 2: finish
 __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
   const uint4 *s = reinterpret_cast<const uint4 *>(p);
@@ -236,7 +265,7 @@ __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
 // One thread owns HS_FINISH_GROUP consecutive records: prefix products of their Z's, ONE inversion, back-substitution,
 // affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into one bitmap word.
 __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_t n, const fe *__restrict__ xyz, const uint8_t *__restrict__ meta,
-                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out) {
+                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out, const peer_route P) {
   const size_t t = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
   const size_t first = t * HS_FINISH_GROUP;
   uint32_t bits = 0;
@@ -279,7 +308,15 @@ __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_
   }
   // lanes 2j and 2j+1 hold bits [32j .. 32j+15] and [32j+16 .. 32j+31] of word (t/2)
   const uint32_t other = __shfl_xor_sync(0xffffffffu, bits, 1);
-  if ((threadIdx.x & 1) == 0 && first < n) bitmap[t >> 1] = bits | (other << 16);
+  if ((threadIdx.x & 1) == 0 && first < n) {
+    const uint32_t word = bits | (other << 16);
+    if (P.n == 0) {
+      bitmap[t >> 1] = word;
+    } else {
+#pragma unroll 1
+      for (int p = 0; p < P.n; p++) P.buf[p][P.word_offset + (t >> 1)] = word;  // fused all-gather: one NVLink store per peer
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ table construction
@@ -354,6 +391,14 @@ struct hs_ctx {
   dev_buf in[2], digest[2], xyz, meta, vidx, miss, out;
   uint32_t *d_miss_count = nullptr;
   uint32_t *h_miss_count = nullptr;  // pinned
+  // multi-GPU peer routing
+  peer_route peers{};
+  int peer_rank = 0;
+  size_t peer_total_words = 0;
+  uint32_t *peer_own = nullptr;       // cudaMalloc'd: [total_words][HS_MAX_PEERS flags][timeout flag]
+  void *peer_mapped[HS_MAX_PEERS] = {};
+  bool peer_armed = false;
+  uint32_t peer_epoch = 0;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::string err = "ok";
@@ -447,9 +492,20 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     HS_CUDA(c, cudaGetLastError());
   }
   const size_t fin_threads = (n + HS_FINISH_GROUP - 1) / HS_FINISH_GROUP;
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, nullptr);
+  peer_route P{};
+  if (c->peer_armed) {
+    P = c->peers;
+    c->peer_armed = false;
+  }
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, nullptr, P);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
+  if (P.n) {
+    k_peer_signal<<<1, HS_MAX_PEERS, 0, stream>>>(P, c->peer_total_words, c->peer_rank, c->peer_epoch);
+    k_peer_wait<<<1, HS_MAX_PEERS, 0, stream>>>(c->peer_own + c->peer_total_words, P.n, c->peer_epoch, c->peer_own + c->peer_total_words + HS_MAX_PEERS);
+    c->launches += 2;
+    HS_CUDA(c, cudaGetLastError());
+  }
   return HS_OK;
 }
 
@@ -525,6 +581,9 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_miss_count);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
   for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->xyz, &c->meta, &c->vidx, &c->miss, &c->out}) cudaFree(b->p);
+  for (int p = 0; p < HS_MAX_PEERS; p++)
+    if (c->peer_mapped[p]) cudaIpcCloseMemHandle(c->peer_mapped[p]);
+  cudaFree(c->peer_own);
   for (int i = 0; i < 2; i++) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
@@ -665,6 +724,58 @@ int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const voi
   HS_CUDA(c, cudaGetLastError());
   in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, (const uint32_t *)d_vidx, (const uint8_t *)d_digests, 32, nullptr, nullptr, 32, 0};
   return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, d_vidx != nullptr);
+}
+
+// ---- multi-GPU peer routing (one process per GPU; handles are exchanged by the host, e.g. torch.distributed.all_gather_object)
+int hs_peer_setup(hs_ctx *c, int rank, int world, size_t total_words, uint8_t handle_out[64]) {
+  if (!c || world < 1 || world > HS_MAX_PEERS || rank < 0 || rank >= world || !handle_out) return fail(c, HS_ERR_ARG, "hs_peer_setup: bad argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  if (c->peer_own) return fail(c, HS_ERR_ARG, "hs_peer_setup: already set up");
+  const size_t bytes = (total_words + HS_MAX_PEERS + 16) * 4;
+  HS_CUDA(c, cudaMalloc(&c->peer_own, bytes));
+  HS_CUDA(c, cudaMemset(c->peer_own, 0, bytes));
+  cudaIpcMemHandle_t h;
+  HS_CUDA(c, cudaIpcGetMemHandle(&h, c->peer_own));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  c->peer_rank = rank;
+  c->peer_total_words = total_words;
+  c->peers = peer_route{};
+  c->peers.n = world;
+  c->peers.buf[rank] = c->peer_own;
+  return HS_OK;
+}
+int hs_peer_open(hs_ctx *c, int peer_rank, const uint8_t handle[64]) {
+  if (!c || !handle || peer_rank < 0 || peer_rank >= c->peers.n || peer_rank == c->peer_rank) return fail(c, HS_ERR_ARG, "hs_peer_open: bad argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void *p = nullptr;
+  HS_CUDA(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer_mapped[peer_rank] = p;
+  c->peers.buf[peer_rank] = (uint32_t *)p;
+  return HS_OK;
+}
+/* Arms the NEXT `_dev` verify call on this context: its bitmap goes to every rank's buffer at word_offset (fused all-gather). */
+int hs_peer_next(hs_ctx *c, size_t word_offset, uint32_t epoch) {
+  if (!c || !c->peer_own) return fail(c, HS_ERR_ARG, "hs_peer_next: peers not set up");
+  for (int p = 0; p < c->peers.n; p++)
+    if (!c->peers.buf[p]) return fail(c, HS_ERR_ARG, "hs_peer_next: a peer buffer is not mapped");
+  c->peers.word_offset = word_offset;
+  c->peer_epoch = epoch;
+  c->peer_armed = true;
+  return HS_OK;
+}
+/* Device pointer of this rank's copy of the full bitmap, and whether a peer wait ever timed out. */
+void *hs_peer_bitmap(hs_ctx *c) { return c ? (void *)c->peer_own : nullptr; }
+int hs_peer_timed_out(hs_ctx *c) {
+  if (!c || !c->peer_own) return 0;
+  uint32_t v = 0;
+  cudaSetDevice(c->device);
+  cudaMemcpy(&v, c->peer_own + c->peer_total_words + HS_MAX_PEERS, 4, cudaMemcpyDeviceToHost);
+  return (int)v;
 }
 
 // ---- host-pointer entry points

@@ -41,3 +41,39 @@ def verify_sharded(verify_fn, n, rank, world, device=None, group=None):
         words = words.to(device)
     full = all_gather_bitmap(words, n, world, group)
     return np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+
+
+class PeerAllGather:
+    """Fused all-gather of the accept bitmap: the verify finish kernel stores its words straight into every rank's result
+    buffer over NVLink (include/hs_crypto.h, hs_peer_*).  `ncclAllGather` (all_gather_bitmap above) is the baseline it replaces."""
+
+    def __init__(self, engine, n_total, rank, world):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        self.e, self.rank, self.world, self.n = engine, rank, world, n_total
+        self.per_words = shard_range(n_total, 0, world)[2] // 32
+        self.total_words = self.per_words * world
+        h = (ctypes.c_uint8 * 64)()
+        engine._check(engine.lib.hs_peer_setup(engine.h, rank, world, self.total_words, h), "hs_peer_setup")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        for p, hp in enumerate(handles):
+            if p != rank:
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(hp)
+                engine._check(engine.lib.hs_peer_open(engine.h, p, buf), "hs_peer_open")
+        dist.barrier()
+        self.epoch = 0
+        ptr = engine.lib.hs_peer_bitmap(engine.h)
+        # zero-copy torch view of this rank's full-bitmap buffer
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (self.total_words,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+        self.full = torch.as_tensor(_Arr(), device=torch.device("cuda", engine.device))
+
+    def arm(self):
+        """Call right before the engine's `_dev` verify of this rank's shard."""
+        self.epoch += 1
+        self.e._check(self.e.lib.hs_peer_next(self.e.h, self.rank * self.per_words, self.epoch), "hs_peer_next")
+
+    def bitmap(self):
+        return self.full[: (self.n + 31) // 32] if self.world * self.per_words * 32 >= self.n else self.full

@@ -110,6 +110,18 @@ int hs_digest32_dev(hs_ctx *ctx, const void *d_data, const void *d_off, size_t n
 int hs_verify_msgs_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk_or_null, const void *d_validator_idx_or_null, const void *d_msgs,
                        size_t msg_len, size_t n, uint32_t mode, void *d_digests, void *d_bitmap, void *stream);
 
+/* ---- multi-GPU: fused all-gather of the accept bitmap (one process per GPU, same node, NVLink) ------------------------
+ * Each rank creates a result buffer for the GLOBAL bitmap (total_words) and exports a 64-byte CUDA-IPC handle; the host
+ * exchanges handles (e.g. torch.distributed.all_gather_object) and opens every peer's.  hs_peer_next() then arms the next
+ * `_dev` verify call: its finish kernel stores each bitmap word it produces directly into EVERY rank's buffer at
+ * word_offset (P2P stores over NVLink), signals the peers and waits for theirs — after the call (stream order) the buffer
+ * returned by hs_peer_bitmap() holds every rank's verdicts for that epoch.  Epochs must increase by one per armed call. */
+int hs_peer_setup(hs_ctx *ctx, int rank, int world, size_t total_words, uint8_t handle_out[64]);
+int hs_peer_open(hs_ctx *ctx, int peer_rank, const uint8_t handle[64]);
+int hs_peer_next(hs_ctx *ctx, size_t word_offset, uint32_t epoch);
+void *hs_peer_bitmap(hs_ctx *ctx);
+int hs_peer_timed_out(hs_ctx *ctx);
+
 #ifdef __cplusplus
 }
 #endif
