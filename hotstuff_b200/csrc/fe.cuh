@@ -15,10 +15,8 @@
 
 #if defined(__CUDACC__)
 #define HS_HD __host__ __device__ __forceinline__
-#define HS_D __device__ __forceinline__
 #else
 #define HS_HD inline
-#define HS_D inline
 #endif
 
 #if defined(__CUDA_ARCH__)

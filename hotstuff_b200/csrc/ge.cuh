@@ -88,20 +88,7 @@ HS_HD void ge_dbl(ge_ext &r, const ge_ext &p) {
   ge_p1p1_to_ext(r, c);
 }
 
-// mixed addition with an affine Niels point (7M); complete for every input on the curve
-HS_HD void ge_madd_p1p1(ge_p1p1 &c, const ge_ext &p, const ge_niels &q) {
-  fe a, b, t, dd;
-  fe_sub(t, p.Y, p.X);
-  fe_mul(a, t, q.ymx);
-  fe_add(t, p.Y, p.X);
-  fe_mul(b, t, q.ypx);
-  fe_mul(t, p.T, q.xy2d);
-  fe_add(dd, p.Z, p.Z);
-  fe_sub(c.E, b, a);
-  fe_add(c.H, b, a);
-  fe_sub(c.F, dd, t);
-  fe_add(c.G, dd, t);
-}
+// Mixed addition with an affine Niels point (7M); complete for every input on the curve.
 // r = p + (neg ? -q : q) without negating a field element: -q = (ymx, ypx, -xy2d), and -xy2d only swaps F and G.
 HS_HD void ge_madd_signed_p1p1(ge_p1p1 &c, const ge_ext &p, const ge_niels &q, uint32_t neg) {
   fe a, b, t, dd, m0, m1;
@@ -122,11 +109,6 @@ HS_HD void ge_madd_signed_p1p1(ge_p1p1 &c, const ge_ext &p, const ge_niels &q, u
 HS_HD void ge_madd_signed(ge_ext &r, const ge_ext &p, const ge_niels &q, uint32_t neg) {
   ge_p1p1 c;
   ge_madd_signed_p1p1(c, p, q, neg);
-  ge_p1p1_to_ext(r, c);
-}
-HS_HD void ge_madd(ge_ext &r, const ge_ext &p, const ge_niels &q) {
-  ge_p1p1 c;
-  ge_madd_p1p1(c, p, q);
   ge_p1p1_to_ext(r, c);
 }
 // addition with a projective cached point (8M)
@@ -174,12 +156,6 @@ HS_HD void ge_niels_identity(ge_niels &r) {
   fe_set1(r.ypx);
   fe_set1(r.ymx);
   fe_set0(r.xy2d);
-}
-HS_HD void ge_niels_cneg(ge_niels &q, uint32_t neg) {
-  fe_cswap(q.ypx, q.ymx, neg);
-  fe nt;
-  fe_neg(nt, q.xy2d);
-  fe_select(q.xy2d, q.xy2d, nt, neg);
 }
 // affine (x, y) -> Niels
 HS_HD void ge_affine_to_niels(ge_niels &r, const fe &x, const fe &y) {

@@ -248,7 +248,7 @@ __global__ void k_peer_wait(const uint32_t *flags, int n, uint32_t epoch, uint32
   const int p = threadIdx.x;
   if (p >= n) return;
   uint32_t v = 0;
-  for (long long spin = 0; spin < (1ll << 27); spin++) {  // bounded: a missing peer becomes an error, never a hang
+  for (long long spin = 0; spin < (1ll << 24); spin++) {  // bounded (~5 s): a missing peer becomes an error, never a hang
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
     if ((int32_t)(v - epoch) >= 0) return;
     __nanosleep(200);
@@ -262,28 +262,52 @@ __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
   uint4 a = s[0], b = s[1];
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
 }
-// One thread owns HS_FINISH_GROUP consecutive records: prefix products of their Z's, ONE inversion, back-substitution,
-// affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into one bitmap word.
+// One thread owns HS_FINISH_GROUP (16) consecutive records and a block owns 2,048.  Montgomery's trick at two levels so that ONE
+// field inversion per 64 records is executed (by warp 0, lane l inverting the product of threads 4l..4l+3) instead of one
+// per thread: phase A prefix products of the thread's 16 Z's; phase B the block-level inversion through shared memory;
+// phase C back-substitution + affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into
+// one bitmap word, which goes to the local bitmap or — armed by hs_peer_next — straight into every peer's buffer.
 __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_t n, const fe *__restrict__ xyz, const uint8_t *__restrict__ meta,
                                                                uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out, const peer_route P) {
+  __shared__ fe tot[HS_THREADS];
   const size_t t = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
   const size_t first = t * HS_FINISH_GROUP;
-  uint32_t bits = 0;
-  if (first < n) {
-    const int cnt = (int)((n - first < HS_FINISH_GROUP) ? (n - first) : HS_FINISH_GROUP);
-    fe prod[HS_FINISH_GROUP];
-    fe run;
-    fe_set1(run);
+  const int cnt = (first < n) ? (int)((n - first < HS_FINISH_GROUP) ? (n - first) : HS_FINISH_GROUP) : 0;
+  fe prod[HS_FINISH_GROUP];
+  fe run;
+  fe_set1(run);
 #pragma unroll 1
-    for (int c = 0; c < cnt; c++) {
-      fe Z;
-      fe_load_global(Z, xyz + (first + c) * 3 + 2);
-      if (fe_is_zero(Z)) fe_set1(Z);  // cannot happen for curve points; keeps one bad record from poisoning the group
-      fe_mul(run, run, Z);
-      prod[c] = run;
-    }
-    fe u;
-    fe_invert(u, run);
+  for (int c = 0; c < cnt; c++) {
+    fe Z;
+    fe_load_global(Z, xyz + (first + c) * 3 + 2);
+    if (fe_is_zero(Z)) fe_set1(Z);  // cannot happen for curve points; keeps one bad record from poisoning the group
+    fe_mul(run, run, Z);
+    prod[c] = run;
+  }
+  tot[threadIdx.x] = run;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int b = threadIdx.x * 4;
+    fe q0 = tot[b], q1, q2, q3, inv, u;
+    fe_mul(q1, q0, tot[b + 1]);
+    fe_mul(q2, q1, tot[b + 2]);
+    fe_mul(q3, q2, tot[b + 3]);
+    fe_invert(inv, q3);
+    fe_mul(u, inv, q2);        // 1 / tot[b+3]
+    fe_mul(inv, inv, tot[b + 3]);
+    tot[b + 3] = u;
+    fe_mul(u, inv, q1);        // 1 / tot[b+2]
+    fe_mul(inv, inv, tot[b + 2]);
+    tot[b + 2] = u;
+    fe_mul(u, inv, q0);        // 1 / tot[b+1]
+    fe_mul(inv, inv, tot[b + 1]);
+    tot[b + 1] = u;
+    tot[b] = inv;              // 1 / tot[b]
+  }
+  __syncthreads();
+  uint32_t bits = 0;
+  if (cnt) {
+    fe u = tot[threadIdx.x];
 #pragma unroll 1
     for (int c = cnt - 1; c >= 0; c--) {
       const size_t i = first + c;

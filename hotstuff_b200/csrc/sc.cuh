@@ -139,14 +139,6 @@ HS_HD void sc_recode(sc_recoded<W> &out, const uint32_t (&s)[8]) {
     acc >>= 32;
   }
 }
-template <int W>
-HS_HD int sc_digit(const sc_recoded<W> &r, int i) {
-  int bit = W * i;
-  int limb = bit >> 5, sh = bit & 31;
-  uint64_t two = (uint64_t)r.u[limb] | ((uint64_t)((limb + 1 < 9) ? r.u[limb + 1] : 0u) << 32);
-  uint32_t raw = (uint32_t)(two >> sh) & ((1u << W) - 1u);
-  return (int)raw - (1 << (W - 1));
-}
 
 // ---- runtime-width variant (the comb tables' window widths are chosen per context / per committee size)
 HS_HD int sc_ndigits_rt(int W) {
