@@ -272,7 +272,11 @@ def run_qc(args):
     pag = None
     if world > 1 and args.collective == "peer":
         from hotstuff_b200.sharding import PeerAllGather
-        pag = PeerAllGather(eng, n, rank, world)
+        try:
+            pag = PeerAllGather(eng, n, rank, world)
+        except RuntimeError as ex:
+            if rank == 0:
+                print("peer all-gather unavailable, using ncclAllGather: %s" % ex, file=sys.stderr)
 
     def step():
         eng.digest32_dev(d_pre, d_off, d_dig, args.qcs)                                    # QC::digest for every certificate
@@ -398,7 +402,12 @@ def main():
     pag = None
     if world > 1 and args.collective == "peer":
         from hotstuff_b200.sharding import PeerAllGather
-        pag = PeerAllGather(eng, n * world, rank, world)
+        try:
+            pag = PeerAllGather(eng, n * world, rank, world)
+        except RuntimeError as ex:     # raised on every rank together: fall back to the NCCL collective
+            args.collective = "nccl"
+            if rank == 0:
+                print("peer all-gather unavailable, using ncclAllGather: %s" % ex, file=sys.stderr)
 
     def step_resident():
         if pag is not None:

@@ -48,6 +48,8 @@ class PeerAllGather:
     buffer over NVLink (include/hs_crypto.h, hs_peer_*).  `ncclAllGather` (all_gather_bitmap above) is the baseline it replaces."""
 
     def __init__(self, engine, n_total, rank, world):
+        """Collective constructor (every rank calls it).  Raises RuntimeError ON EVERY RANK if any rank cannot set up or map
+        the CUDA-IPC buffers, so callers can fall back to all_gather_bitmap() consistently."""
         import ctypes
         import torch
         import torch.distributed as dist
@@ -55,14 +57,20 @@ class PeerAllGather:
         self.per_words = shard_range(n_total, 0, world)[2] // 32
         self.total_words = self.per_words * world
         h = (ctypes.c_uint8 * 64)()
-        engine._check(engine.lib.hs_peer_setup(engine.h, rank, world, self.total_words, h), "hs_peer_setup")
+        ok = engine.lib.hs_peer_setup(engine.h, rank, world, self.total_words, h) == 0
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(h))
-        for p, hp in enumerate(handles):
-            if p != rank:
-                buf = (ctypes.c_uint8 * 64).from_buffer_copy(hp)
-                engine._check(engine.lib.hs_peer_open(engine.h, p, buf), "hs_peer_open")
-        dist.barrier()
+        dist.all_gather_object(handles, bytes(h) if ok else None)
+        if ok and all(x is not None for x in handles):
+            for p, hp in enumerate(handles):
+                if p != rank:
+                    buf = (ctypes.c_uint8 * 64).from_buffer_copy(hp)
+                    ok = ok and engine.lib.hs_peer_open(engine.h, p, buf) == 0
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", engine.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise RuntimeError("peer buffers could not be set up on every rank: " + engine.lib.hs_last_error(engine.h).decode())
         self.epoch = 0
         ptr = engine.lib.hs_peer_bitmap(engine.h)
         # zero-copy torch view of this rank's full-bitmap buffer
