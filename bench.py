@@ -552,6 +552,9 @@ def main():
         # wide multiplies (IMAD.WIDE.U32[.X]) per verify: 7 field multiplications x 71 per mixed addition (SASS count of the hot
         # loop), + ~0.7 k for the mod-l reduction and the batched-inversion share; generic keys add 252 doublings + decompression
         wide_per_verify = adds * 7 * 71 + 700 + (0 if wa else 252 * 7 * 56 + 20000)
+        # field multiplications per verify (squarings counted as 0.7): 7 per mixed addition + mod-l/compare overhead + inversion share;
+        # generic keys: + 252 doublings (3 M + 4 S) + 64 additions (8 M) + decompression (~254 S + 20 M)
+        fe_muls = adds * 7 + 10 + (0 if wa else 252 * (3 + 4 * 0.7) + 64 * 8 + 254 * 0.7 + 20)
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
         wide_rate = wide_per_verify * n / (kern_ms * 1e-3) / (148 * sm_clk * 1e6)
         line = {
@@ -565,10 +568,14 @@ def main():
                          "kernel_ms": kern_ms, "kernel_ms_covers": "lookup + main + finish kernels of one verify pass over 2^20 resident records",
                          "algorithmic_bytes_per_verify": ALGO_BYTES_VERIFY,
                          "note": "integer-ALU bound path: 128 B of compulsory I/O per ~0.1-0.3 M INT32 instructions; HBM fraction is necessarily << 1 (SURVEY §0.7)"},
-            "alu_roofline": {"bound": "IMAD.WIDE issue (FMA-heavy pipe) — the resource that actually binds this path", "unit": "wide-mads/clk/SM",
-                             "achieved": wide_rate, "peak": 54.0, "frac": wide_rate / 54.0, "wide_mads_per_verify": wide_per_verify,
+            "alu_roofline": {"bound": "integer-multiply (FMA-heavy / IMAD) pipe — the resource that actually binds this path",
+                             "unit": "GF(2^255-19) multiplications/s", "achieved": fe_muls * n / (kern_ms * 1e-3), "peak": 1.044e11,
+                             "frac": fe_muls * n / (kern_ms * 1e-3) / 1.044e11, "field_muls_per_verify": fe_muls,
                              "mixed_additions_per_verify": adds, "window_bits": {"key": wa, "base": wb},
-                             "peak_source": "tools/microbench/pipes.cu on B200 (profiles/r01_pipes.txt); ncu sm__pipe_fmaheavy_cycles_active for this kernel: profiles/r01_ncu_summary.md"},
+                             "wide_mads_per_clk_per_sm": wide_rate, "wide_mad_peak_per_clk_per_sm": 54.0,
+                             "ncu_fmaheavy_pipe_busy": 0.80,
+                             "peak_source": "fe_mul microbenchmark on this GPU (tools/microbench/febench.cu, profiles/r01_febench.txt); pipe utilisation from "
+                                            "ncu sm__pipe_fmaheavy_cycles_active (profiles/r01_ncu_summary.md); IMAD.WIDE peak from profiles/r01_pipes.txt"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -174,7 +174,21 @@ static void fe_mul(fe *r, const fe *a, const fe *b) {
   r->v[0] += 19 * (uint64_t)(t4 >> 51); r->v[4] = (uint64_t)t4 & M51;
   r->v[1] += r->v[0] >> 51; r->v[0] &= M51;
 }
-static void fe_sq(fe *r, const fe *a) { fe_mul(r, a, a); }
+static void fe_sq(fe *r, const fe *a) { /* dedicated squaring: 15 products instead of 25 */
+  const uint64_t *x = a->v;
+  uint64_t d0 = 2 * x[0], d1 = 2 * x[1], d2 = 2 * x[2], x3_19 = 19 * x[3], x4_19 = 19 * x[4];
+  u128 t0 = (u128)x[0] * x[0] + (u128)d1 * x4_19 + (u128)d2 * x3_19;
+  u128 t1 = (u128)d0 * x[1] + (u128)d2 * x4_19 + (u128)x[3] * x3_19;
+  u128 t2 = (u128)d0 * x[2] + (u128)x[1] * x[1] + (u128)(2 * x[3]) * x4_19;
+  u128 t3 = (u128)d0 * x[3] + (u128)d1 * x[2] + (u128)x[4] * x4_19;
+  u128 t4 = (u128)d0 * x[4] + (u128)d1 * x[3] + (u128)x[2] * x[2];
+  t1 += (uint64_t)(t0 >> 51); r->v[0] = (uint64_t)t0 & M51;
+  t2 += (uint64_t)(t1 >> 51); r->v[1] = (uint64_t)t1 & M51;
+  t3 += (uint64_t)(t2 >> 51); r->v[2] = (uint64_t)t2 & M51;
+  t4 += (uint64_t)(t3 >> 51); r->v[3] = (uint64_t)t3 & M51;
+  r->v[0] += 19 * (uint64_t)(t4 >> 51); r->v[4] = (uint64_t)t4 & M51;
+  r->v[1] += r->v[0] >> 51; r->v[0] &= M51;
+}
 static void fe_sqn(fe *r, const fe *a, int n) { fe_sq(r, a); for (int i = 1; i < n; i++) fe_sq(r, r); }
 
 /* z^(2^250 - 1) and z^11 through the usual 2,9,11,2^5-1,2^10-1,... ladder */
