@@ -168,3 +168,78 @@ def to_rec128(w):
     recs[:, 64:96] = w["pk"]
     recs[:, 96:] = w["msgs"].reshape(n, 32)
     return recs
+
+
+def make_adversarial(oracle, n, seed=1):
+    """Randomised adversarial (sig, pk, 32-byte msg) records for differential testing: valid signatures mutated along the
+    axes where Ed25519 implementations disagree — torsion components added to A and/or R (with the signature recomputed
+    for the mixed key so the cofactorless equation may or may not hold), non-canonical S (S + l), small-order A / R,
+    random byte strings as A / R (about half do not decompress), non-canonical field encodings, bit flips."""
+    import hashlib
+    rng = np.random.default_rng(seed)
+    Y8 = 0x05fc536d880238b13933c6d305acdfd5f098eff289f4c345b027b2c28f95e826
+    tors = []
+    for ty in (0, 1, P - 1, P, P + 1, Y8, P - Y8):
+        for sign in (0, 1):
+            e = bytearray(int(ty).to_bytes(32, "little"))
+            e[31] |= sign << 7
+            tors.append(bytes(e))
+    B_enc = int("6666666666666666666666666666666666666666666666666666666666666658", 16).to_bytes(32, "little")
+    nk = 8
+    seeds = [rng.bytes(32) for _ in range(nk)]
+    pks = [oracle.keygen(s) for s in seeds]
+    scal = []
+    for s in seeds:
+        h = hashlib.sha512(s).digest()
+        a = int.from_bytes(bytes([h[0] & 248]) + h[1:31] + bytes([(h[31] & 127) | 64]), "little")
+        scal.append((a, h[32:]))
+    recs = np.zeros((n, 128), dtype=np.uint8)
+    kinds = rng.integers(0, 10, n)
+    for i in range(n):
+        k = int(rng.integers(0, nk))
+        m = rng.bytes(32)
+        a, prefix = scal[k]
+        A = pks[k]
+        kind = int(kinds[i])
+        if kind in (1, 2):                      # mixed-order key (and sometimes nonce): sign for A' = A + T
+            A = oracle.point_add(pks[k], tors[int(rng.integers(0, len(tors)))])
+        r = int.from_bytes(hashlib.sha512(prefix + m).digest(), "little") % L_ORDER
+        R = oracle.scalarmult(r, B_enc)
+        if kind == 2:
+            R = oracle.point_add(R, tors[int(rng.integers(0, len(tors)))])
+        kk = oracle.sc_reduce64(hashlib.sha512(R + A + m).digest())
+        S = (r + kk * a) % L_ORDER
+        sig = bytearray(R + int(S).to_bytes(32, "little"))
+        pk = bytearray(A)
+        if kind == 3 and S + L_ORDER < 2**256:  # non-canonical S
+            sig[32:] = int(S + L_ORDER).to_bytes(32, "little")
+        elif kind == 4:                         # small-order A or R
+            if rng.integers(0, 2):
+                pk = bytearray(tors[int(rng.integers(0, len(tors)))])
+            else:
+                sig[:32] = tors[int(rng.integers(0, len(tors)))]
+        elif kind == 5:                         # random bytes as A or R
+            if rng.integers(0, 2):
+                pk = bytearray(rng.bytes(32))
+            else:
+                sig[:32] = rng.bytes(32)
+        elif kind == 6:                         # single bit flip anywhere
+            b = int(rng.integers(0, 128 * 8))
+            buf = bytearray(bytes(sig) + bytes(pk) + m)
+            buf[b >> 3] ^= 1 << (b & 7)
+            sig, pk, m = buf[:64], buf[64:96], bytes(buf[96:])
+        elif kind == 7:                         # high / non-canonical field bits
+            which = int(rng.integers(0, 3))
+            if which == 0:
+                pk[31] ^= 0x80
+            elif which == 1:
+                sig[31] ^= 0x80
+            else:
+                sig[63] |= int(rng.integers(1, 8)) << 5
+        elif kind == 8:                         # identity key: R = [S]B verifies for any message in batch-eq mode
+            pk = bytearray((1).to_bytes(32, "little"))
+            sig = bytearray(oracle.scalarmult(r, B_enc) + int(r).to_bytes(32, "little"))
+        recs[i, :64] = np.frombuffer(bytes(sig), np.uint8)
+        recs[i, 64:96] = np.frombuffer(bytes(pk), np.uint8)
+        recs[i, 96:] = np.frombuffer(m, np.uint8)
+    return recs

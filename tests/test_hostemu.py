@@ -116,3 +116,17 @@ def test_random_parity_with_oracle(hostemu, oracle):
         sig = oracle.sign(seed, m)
         for s, p, mm in ((sig, pk, m), (bytes([sig[0] ^ 1]) + sig[1:], pk, m), (sig, bytes([pk[0] ^ 2]) + pk[1:], m), (sig[:40] + bytes([sig[40] ^ 8]) + sig[41:], pk, m)):
             assert hostemu.emu_verify_generic(s, p, mm, ctypes.c_uint64(len(mm))) == oracle.flags(s, p, mm) & ~R_OK
+
+
+def test_randomised_adversarial_differential_hostemu(hostemu, oracle):
+    """Same randomised adversarial generator as the GPU test, at a size the host emulation finishes quickly."""
+    from oracle_api import make_adversarial
+    hostemu.emu_set_windows(10, 12)
+    recs = make_adversarial(oracle, 600, seed=7)
+    agree = 0
+    for r in recs:
+        sig, pk, m = r[:64].tobytes(), r[64:96].tobytes(), r[96:].tobytes()
+        want = oracle.flags(sig, pk, m, fast=True) & ~R_OK
+        assert hostemu.emu_verify_generic(sig, pk, m, ctypes.c_uint64(32)) == want
+        agree += 1
+    assert agree == 600
