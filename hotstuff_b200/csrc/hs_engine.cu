@@ -3,13 +3,15 @@
 // Hot path of asonnino/hotstuff's crypto crate (crypto/src/lib.rs:200-219 + the SHA-512 Digest call sites) rebuilt for
 // B200.  No CPU path: if CUDA fails the call returns an error and the caller must reject.
 //
-// Pipeline of one verify call (all on one stream):
-//   k_key_lookup      pk bytes -> committee index through a device hash table (skipped when the caller gives indices)
-//   k_verify_main<C>  committee keys: SHA-512(R||A||M) -> k mod l -> [k](-A) + [S]B by table gathers only
-//                     (22 + 16 mixed additions, no doublings, no decompression) -> projective (X:Y:Z) + meta
-//   k_verify_main<G>  records whose key is not registered (compacted list): decompress A, radix-16 window for [k](-A)
-//   k_verify_finish   Montgomery-batched inversion of 16 Z's per thread, affine compare with R's encoding,
-//                     small-order rule, 32 verdicts -> one bitmap word
+// Pipeline of one verify call:
+//   k_key_lookup      pk bytes -> committee index through a device hash table; misses -> compacted list
+//                     (skipped when the caller gives validator indices)
+//   k_verify_main<C>  registered keys: SHA-512(R||A||M) -> k mod l -> [k](-A) + [S]B by table gathers only
+//                     (e.g. 17 + 11 mixed additions for 4,096 keys; no doublings, no decompression) -> (X:Y:Z) + meta
+//   k_verify_main<G>  records whose key is not registered: decompress A, radix-16 window for [k](-A); runs over the
+//                     compacted list on a high-priority side stream, concurrently with the pass above
+//   k_verify_finish   two-level Montgomery-batched inversion, affine compare with R's encoding, small-order rule,
+//                     32 verdicts -> one bitmap word, stored locally or into every peer GPU's buffer (fused all-gather)
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>

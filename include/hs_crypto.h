@@ -81,7 +81,7 @@ int hs_verify_batch_shared_msg(hs_ctx *ctx, const uint8_t digest[32], const hs_v
                                uint32_t *out_bitmap_or_null);
 
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
-/* Decompresses every key and builds its comb table in HBM (w = 16: 48 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
+/* Decompresses every key and builds its comb table in HBM (window 16 bits: 48 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
 int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
 /* Vote i is (validator_idx[i], sig[i]) over digests[msg_idx[i]].  msg_idx may be NULL when n_msgs == 1. */
