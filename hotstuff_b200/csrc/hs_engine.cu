@@ -393,6 +393,18 @@ __global__ void __launch_bounds__(HS_THREADS) k_digest32(const uint8_t *__restri
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// ------------------------------------------------------------------------------------------------ per-QC AND
+// vote i belongs to certificate qc_idx[i]; a rejected vote clears its certificate's bit (qc bitmap pre-set to all ones)
+__global__ void __launch_bounds__(256) k_qc_and(const uint32_t *__restrict__ vote_bitmap, const uint32_t *__restrict__ qc_idx, size_t n_votes,
+                                                size_t n_qc, uint32_t *__restrict__ qc_bitmap) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n_votes) return;
+  if (!((vote_bitmap[i >> 5] >> (i & 31)) & 1u)) {
+    const uint32_t j = qc_idx[i];
+    if (j < n_qc) atomicAnd(qc_bitmap + (j >> 5), ~(1u << (j & 31)));
+  }
+}
+
 // ================================================================================================ host side
 struct dev_buf {
   void *p = nullptr;
@@ -750,6 +762,46 @@ int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const voi
   HS_CUDA(c, cudaGetLastError());
   in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, (const uint32_t *)d_vidx, (const uint8_t *)d_digests, 32, nullptr, nullptr, 32, 0};
   return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, d_vidx != nullptr);
+}
+
+// ---- QC::verify for many certificates (consensus/src/messages.rs:180-208)
+int hs_verify_qcs(hs_ctx *c, const uint8_t *preimages, size_t n_qc, const uint8_t *pk, const uint32_t *vidx, const uint8_t *sig,
+                  const uint32_t *qc_idx, size_t n_votes, uint32_t *out_vote_bitmap, uint32_t *out_qc_bitmap) {
+  if (!c || !out_qc_bitmap || (n_qc && !preimages) || (n_votes && (!sig || !qc_idx || (!pk && !vidx) || n_qc == 0)))
+    return fail(c, HS_ERR_ARG, "hs_verify_qcs: bad argument");
+  const size_t qc_words = (n_qc + 31) / 32, vote_words = (n_votes + 31) / 32;
+  for (size_t w = 0; w < qc_words; w++) out_qc_bitmap[w] = (w == qc_words - 1 && (n_qc & 31)) ? ((1u << (n_qc & 31)) - 1u) : 0xffffffffu;
+  if (n_votes == 0) return HS_OK;
+  for (size_t i = 0; i < n_votes; i++)
+    if (qc_idx[i] >= n_qc) return fail(c, HS_ERR_ARG, "hs_verify_qcs: qc_idx out of range");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  const size_t key_bytes = pk ? 32 : 4;
+  const size_t o_pre = 0, o_dig = (n_qc * 40 + 15) & ~(size_t)15, o_sig = o_dig + n_qc * 32, o_key = o_sig + n_votes * 64,
+               o_qi = o_key + ((n_votes * key_bytes + 15) & ~(size_t)15), total = o_qi + n_votes * 4;
+  HS_TRY(ensure(c, c->in[0], total));
+  HS_TRY(ensure(c, c->out, (vote_words + qc_words) * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
+  uint32_t *d_votes = (uint32_t *)c->out.p, *d_qc = d_votes + vote_words;
+  HS_CUDA(c, cudaMemcpyAsync(d + o_pre, preimages, n_qc * 40, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig, n_votes * 64, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_key, pk ? (const void *)pk : (const void *)vidx, n_votes * key_bytes, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_qi, qc_idx, n_votes * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d_qc, out_qc_bitmap, qc_words * 4, cudaMemcpyHostToDevice, c->stream));  // all ones (tail cleared)
+  // QC::digest = SHA-512(hash || round_le)[..32] for every certificate (messages.rs:201-208)
+  k_digest32<<<blocks_for(n_qc), HS_THREADS, 0, c->stream>>>(d + o_pre, nullptr, 40, n_qc, (uint32_t *)(d + o_dig));
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  in_layout L{d + o_sig, 64, pk ? d + o_key : nullptr, 32, pk ? nullptr : (const uint32_t *)(d + o_key), d + o_dig, 32, (const uint32_t *)(d + o_qi),
+              nullptr, 32, 0};
+  HS_TRY(run_verify(c, L, n_votes, HS_MODE_BATCH_EQ, d_votes, c->stream, pk == nullptr));
+  k_qc_and<<<blocks_for(n_votes, 256), 256, 0, c->stream>>>(d_votes, (const uint32_t *)(d + o_qi), n_votes, n_qc, d_qc);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  if (out_vote_bitmap) HS_CUDA(c, cudaMemcpyAsync(out_vote_bitmap, d_votes, vote_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out_qc_bitmap, d_qc, qc_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
 }
 
 // ---- multi-GPU peer routing (one process per GPU; handles are exchanged by the host, e.g. torch.distributed.all_gather_object)

@@ -112,6 +112,23 @@ class Engine:
                     "hs_verify_batch_shared_msg")
         return (bool(ok.value), bitmap_to_bools(bm, n)) if want_bitmap else bool(ok.value)
 
+    def verify_qcs(self, preimages, sig, qc_idx, pk=None, validator_idx=None, want_votes=False):
+        """Many QCs in one pass: preimages (n_qc,40) = hash||round_le; vote i -> certificate qc_idx[i].  Returns bool[n_qc]
+        (and bool[n_votes] when want_votes)."""
+        pre = _u8(preimages, 40).reshape(-1, 40)
+        sig = _u8(sig, 64).reshape(-1, 64)
+        n_qc, n = pre.shape[0], sig.shape[0]
+        qi = np.ascontiguousarray(qc_idx, dtype=np.uint32)
+        assert qi.shape[0] == n and (pk is None) != (validator_idx is None)
+        pk = None if pk is None else _u8(pk, 32).reshape(-1, 32)
+        vidx = None if validator_idx is None else np.ascontiguousarray(validator_idx, dtype=np.uint32)
+        qbm = np.zeros(max(1, (n_qc + 31) // 32), dtype=np.uint32)
+        vbm = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32) if want_votes else None
+        self._check(self.lib.hs_verify_qcs(self.h, _ptr(pre) if n_qc else None, n_qc, _ptr(pk), _ptr(vidx), _ptr(sig) if n else None,
+                                           _ptr(qi) if n else None, n, _ptr(vbm), _ptr(qbm)), "hs_verify_qcs")
+        out = bitmap_to_bools(qbm, n_qc)
+        return (out, bitmap_to_bools(vbm, n)) if want_votes else out
+
     def committee_register(self, pks):
         pks = _u8(pks, 32).reshape(-1, 32)
         n = pks.shape[0]

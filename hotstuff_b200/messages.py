@@ -111,23 +111,19 @@ def verify_qcs(qcs, committee, engine=None):
             ok.append(True)
         except ConsensusError:
             ok.append(False)
-    digests = digest_many([vote_preimage(qc.hash, qc.round) for qc in qcs], e)
-    sig, pk, midx = [], [], []
-    for j, qc in enumerate(qcs):
-        if not ok[j]:
-            continue
-        for name, s in qc.votes:
-            sig.append(s.flatten())
+    pre, sig, pk, midx = [], [], [], []
+    live = [j for j, o in enumerate(ok) if o]
+    for new_j, j in enumerate(live):
+        qc = qcs[j]
+        pre.append(vote_preimage(qc.hash, qc.round))
+        for name, s_ in qc.votes:
+            sig.append(s_.flatten())
             pk.append(name.b)
-            midx.append(j)
-    if not sig:
+            midx.append(new_j)
+    if not live:
         return ok
-    n = len(sig)
-    recs = np.zeros((n, 128), dtype=np.uint8)
-    recs[:, :64] = np.frombuffer(b"".join(sig), np.uint8).reshape(n, 64)
-    recs[:, 64:96] = np.frombuffer(b"".join(pk), np.uint8).reshape(n, 32)
-    recs[:, 96:] = np.array([np.frombuffer(digests[j].b, np.uint8) for j in midx])
-    bits = e.verify_rec128(recs, mode=1)                    # verify_batch semantics (cofactorless equation per vote)
-    bad = np.zeros(len(qcs), dtype=bool)
-    np.logical_or.at(bad, np.asarray(midx), ~bits)
-    return [bool(o and not b) for o, b in zip(ok, bad)]
+    good = e.verify_qcs(np.frombuffer(b"".join(pre), np.uint8), np.frombuffer(b"".join(sig), np.uint8), np.asarray(midx, dtype=np.uint32),
+                        pk=np.frombuffer(b"".join(pk), np.uint8))   # digests, votes and the per-QC AND all on the GPU
+    for new_j, j in enumerate(live):
+        ok[j] = bool(good[new_j])
+    return ok

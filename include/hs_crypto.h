@@ -80,6 +80,16 @@ int hs_verify_var(hs_ctx *ctx, const uint8_t *sig, const uint8_t *pk, const uint
 int hs_verify_batch_shared_msg(hs_ctx *ctx, const uint8_t digest[32], const hs_vote *votes, size_t n, int *all_ok,
                                uint32_t *out_bitmap_or_null);
 
+/* ---- QC::verify for many certificates in one pass (consensus/src/messages.rs:180-208) --------------------------------- */
+/* preimages: n_qc x 40 bytes = hash[32] || round_le[8]; the engine computes QC::digest (messages.rs:201-208) on the GPU.
+ * Vote i = (key_i, sig_i) belongs to certificate qc_idx[i]; key_i = pk[i] (32 B each) or, when pk is NULL, committee key
+ * validator_idx[i].  out_qc_bitmap bit j = AND over certificate j's votes of the verify_batch condition (no votes -> 1);
+ * out_vote_bitmap (nullable) = per-vote verdicts.  The stake / duplicate checks of messages.rs:182-194 stay on the host.
+ * This is the view-change burst of SURVEY §3D (every Timeout carries a high_qc) as ONE engine call. */
+int hs_verify_qcs(hs_ctx *ctx, const uint8_t *preimages, size_t n_qc, const uint8_t *pk_or_null, const uint32_t *validator_idx_or_null,
+                  const uint8_t *sig /* n_votes x 64 */, const uint32_t *qc_idx, size_t n_votes, uint32_t *out_vote_bitmap_or_null,
+                  uint32_t *out_qc_bitmap);
+
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
 /* Decompresses every key and builds its comb table in HBM (window 16 bits: 48 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */

@@ -363,3 +363,34 @@ def test_randomised_adversarial_differential(engine, oracle):
     got = engine.verify_committee(inv.astype(np.uint32), recs[:, :64].copy(), recs[:, 96:].copy(), msg_idx=np.arange(len(recs), dtype=np.uint32), mode=0)
     assert (got == want_s).all()
     engine.committee_register(np.zeros((0, 32), np.uint8))
+
+
+def test_verify_qcs_one_pass(engine, oracle):
+    """hs_verify_qcs: QC::digest on the GPU, verify_batch condition per vote, per-QC AND — against the oracle, with key bytes and
+    with validator indices, including a certificate without votes and a certificate with one bad vote."""
+    rng = np.random.default_rng(808)
+    N, Q = 50, 300
+    seeds = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+    pks = oracle.keygen_batch(seeds)
+    pre = np.zeros((Q, 40), dtype=np.uint8)
+    pre[:, :32] = rng.integers(0, 256, (Q, 32), dtype=np.uint8)
+    pre[:, 32:] = np.arange(Q, dtype="<u8").view(np.uint8).reshape(Q, 8)
+    digests = oracle.digest32_batch(pre.reshape(-1), np.arange(Q + 1, dtype=np.uint64) * 40)
+    votes_per = rng.integers(0, 40, Q)
+    votes_per[5] = 0
+    qi = np.repeat(np.arange(Q, dtype=np.uint32), votes_per)
+    n = len(qi)
+    vidx = rng.integers(0, N, n).astype(np.uint32)
+    sig = oracle.sign_batch(seeds, pks, vidx, digests[qi].reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+    bad = rng.choice(n, n // 30, replace=False)
+    sig[bad, rng.integers(0, 64, len(bad))] ^= 0x08
+    want_votes = oracle.verify_rec128(np.concatenate([sig, pks[vidx], digests[qi]], axis=1), mode=1)
+    want_qc = np.ones(Q, dtype=bool)
+    np.logical_and.at(want_qc, qi, want_votes)
+    engine.committee_register(np.zeros((0, 32), np.uint8))
+    got_qc, got_votes = engine.verify_qcs(pre, sig, qi, pk=pks[vidx], want_votes=True)
+    assert (got_votes == want_votes).all() and (got_qc == want_qc).all() and got_qc[5] and (~want_qc).sum() > 20
+    engine.committee_register(pks)
+    assert (engine.verify_qcs(pre, sig, qi, validator_idx=vidx) == want_qc).all()
+    assert (engine.verify_qcs(pre, sig, qi, pk=pks[vidx]) == want_qc).all()
+    engine.committee_register(np.zeros((0, 32), np.uint8))
