@@ -343,10 +343,10 @@ def main():
     ap.add_argument("--n", type=int, default=1 << 20)
     ap.add_argument("--keys", type=int, default=4096)
     ap.add_argument("--msg-len", type=int, default=512)
-    ap.add_argument("--key-mode", default="committee", choices=["committee", "indexed", "generic"],
+    ap.add_argument("--key-mode", default="committee", choices=["committee", "indexed", "generic", "cache"],
                     help="committee: the signer keys are registered once (epoch set-up, untimed); records carry 32-byte keys that the "
                          "engine resolves through its device hash table.  indexed: records carry validator indices.  generic: nothing registered, "
-                         "every key is decompressed per record")
+                         "every key is decompressed per record (key cache off).  cache: nothing registered, the engine learns the keys during warm-up")
     ap.add_argument("--ref-sample", type=int, default=1 << 18)
     ap.add_argument("--cpu-sample", type=int, default=1 << 17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -381,7 +381,7 @@ def main():
     from hotstuff_b200 import Engine, build
     if not os.environ.get("HS_CRYPTO_LIB"):
         build.build_engine()
-    eng = Engine(local_rank)
+    eng = Engine(local_rank, key_cache=(args.key_mode != "generic"))
     n, L = args.n, args.msg_len
     inp = make_inputs(n, args.keys, L, seed=1234 + rank, corrupt_frac=0.01)
     n_bad = int(inp["corrupted"].sum())
@@ -395,7 +395,7 @@ def main():
     words = (n + 31) // 32
     d_bitmap = torch.zeros(words, dtype=torch.int32, device=dev)
     d_all = torch.zeros(words * world, dtype=torch.int32, device=dev)
-    if args.key_mode != "generic":
+    if args.key_mode in ("committee", "indexed"):
         assert eng.committee_register(inp["pks"]).all()
     indexed = args.key_mode == "indexed"
 
@@ -562,7 +562,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": workload_config(args, world), "gpu_launches": int(launches), "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>",
+            "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>", "cached_keys": eng.cached_keys,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s", "traffic": traffic,
                          "kernel_ms": kern_ms, "kernel_ms_covers": "lookup + main + finish kernels of one verify pass over 2^20 resident records",

@@ -13,6 +13,7 @@ SIGNATURES = {
     "hs_ctx_destroy": (None, [c_void_p]),
     "hs_last_error": (ctypes.c_char_p, [c_void_p]),
     "hs_kernel_launches": (c_u64, [c_void_p]),
+    "hs_cached_keys": (c_size_t, [c_void_p]),
     "hs_window_bits": (None, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "hs_host_alloc": (c_void_p, [c_size_t]),
     "hs_host_free": (None, [c_void_p]),

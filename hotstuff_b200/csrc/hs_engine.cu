@@ -29,6 +29,7 @@
 #define HS_THREADS 128
 #define HS_FINISH_GROUP 16  // signatures whose Z's share one inversion
 #define HS_NO_KEY 0xffffffffu
+#define HS_LEARN_MAX 8192u  // unknown keys examined per call
 
 // ------------------------------------------------------------------------------------------------ input layout
 // One descriptor covers every caller-facing layout: packed hs_rec128 records, separate sig/pk arrays with
@@ -119,6 +120,26 @@ __global__ void __launch_bounds__(256) k_key_lookup(in_layout L, size_t n, key_t
   }
   out_vidx[i] = found;
   if (found == HS_NO_KEY) miss_list[atomicAdd(miss_count, 1u)] = (uint32_t)i;  // compacted list for the generic pass
+}
+
+// ------------------------------------------------------------------------------------------------ key cache: collect unknown keys
+// Copies the key bytes of (up to `max_keys`) records that missed the lookup — or, when nothing is cached yet, of the first
+// records of the call — into a compact buffer that is read back asynchronously; the host dedupes them before the NEXT call
+// and builds their tables (hs_engine.cu: learn_process).  miss_count == nullptr: take records 0 .. n-1 directly.
+__global__ void __launch_bounds__(256) k_gather_keys(in_layout L, size_t n, const uint32_t *__restrict__ miss_list,
+                                                     const uint32_t *__restrict__ miss_count, uint32_t max_keys, uint8_t *__restrict__ out_keys,
+                                                     uint32_t *__restrict__ out_n) {
+  const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const size_t avail = miss_count ? (size_t)*miss_count : n;
+  const size_t take = avail < max_keys ? avail : max_keys;
+  if (t == 0) *out_n = (uint32_t)take;
+  if (t >= take) return;
+  const size_t i = miss_count ? miss_list[t] : t;
+  uint32_t k[8];
+  load32(k, L.pk + i * L.pk_stride);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(out_keys + t * 32);
+#pragma unroll
+  for (int j = 0; j < 8; j++) dst[j] = k[j];
 }
 
 // ------------------------------------------------------------------------------------------------ phase 1: main
@@ -429,6 +450,16 @@ struct hs_ctx {
   dev_buf in[2], digest[2], xyz, meta, vidx, miss, out;
   uint32_t *d_miss_count = nullptr;
   uint32_t *h_miss_count = nullptr;  // pinned
+  // key cache: tables for keys that were never registered but keep showing up (learned between calls)
+  bool explicit_committee = false;   // hs_committee_register was called with keys: the set is fixed, nothing is learned
+  bool cache_wanted = true, cache_enabled = true;
+  size_t cache_cap = 4096;           // keys
+  std::vector<uint8_t> h_pks;        // host mirrors of d_pks / d_slots while the cache is in use
+  std::vector<uint32_t> h_slots;
+  uint8_t *d_learn_keys = nullptr, *h_learn_keys = nullptr;
+  uint32_t *d_learn_n = nullptr, *h_learn_n = nullptr;
+  cudaEvent_t ev_learn = nullptr;
+  bool learn_pending = false;
   // multi-GPU peer routing
   peer_route peers{};
   int peer_rank = 0;
@@ -487,16 +518,139 @@ static int launch_build(hs_ctx *c, const uint8_t *d_encs, size_t n_points, int n
   return HS_OK;
 }
 
+static void set_window(comb_params &cp, bool a, int w) {
+  if (a) {
+    cp.wa = w;
+    cp.na = sc_ndigits_rt(w);
+    sc_bias_rt(cp.bias_a, w);
+  } else {
+    cp.wb = w;
+    cp.nb = sc_ndigits_rt(w);
+    sc_bias_rt(cp.bias_b, w);
+  }
+}
+
+// ---- key cache -----------------------------------------------------------------------------------------------------
+static void cache_release(hs_ctx *c) {
+  cudaFree(c->d_pks);
+  cudaFree(c->d_key_flags);
+  cudaFree(c->d_atables);
+  cudaFree(c->d_slots);
+  c->d_pks = nullptr;
+  c->d_key_flags = nullptr;
+  c->d_atables = nullptr;
+  c->d_slots = nullptr;
+  c->n_keys = 0;
+  c->h_pks.clear();
+  c->h_slots.clear();
+}
+// lazily allocate the store for cache_cap learned keys (12-bit windows: 4.1 MB per key, or narrower if memory is short)
+static int cache_allocate(hs_ctx *c) {
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  int wa = 8;
+  for (int w : {12, 10, 8}) {
+    wa = w;
+    if (c->cache_cap * comb_table_entries(w) * sizeof(ge_niels) <= free_b / 2) break;
+  }
+  if (c->cache_cap * comb_table_entries(wa) * sizeof(ge_niels) > free_b / 2 || sc_ndigits_rt(wa) + c->cp.nb > HS_MAX_DIGITS) {
+    c->cache_enabled = false;  // not enough memory: stay on the generic path
+    return HS_OK;
+  }
+  uint32_t cap = 16;
+  while (cap < 2 * c->cache_cap) cap <<= 1;
+  set_window(c->cp, true, wa);
+  c->a_table_entries = comb_table_entries(wa);
+  HS_CUDA(c, cudaMalloc(&c->d_pks, c->cache_cap * 32));
+  HS_CUDA(c, cudaMalloc(&c->d_key_flags, c->cache_cap));
+  HS_CUDA(c, cudaMalloc(&c->d_slots, (size_t)cap * 4));
+  HS_CUDA(c, cudaMalloc(&c->d_atables, c->cache_cap * sizeof(ge_niels) * c->a_table_entries));
+  HS_CUDA(c, cudaMemset(c->d_slots, 0xff, (size_t)cap * 4));
+  c->slot_mask = cap - 1;
+  c->h_slots.assign(cap, HS_NO_KEY);
+  c->h_pks.clear();
+  return HS_OK;
+}
+// Called at the start of a verify pass: if the previous pass left unknown keys behind (already copied to pinned host memory),
+// dedupe them, append the new ones to the store and build their comb tables on `stream` before this pass's lookup runs.
+static int learn_process(hs_ctx *c, cudaStream_t stream) {
+  if (!c->learn_pending) return HS_OK;
+  if (cudaEventQuery(c->ev_learn) != cudaSuccess) return HS_OK;  // copy still in flight: try again on the next call
+  c->learn_pending = false;
+  if (!c->cache_enabled || c->explicit_committee) return HS_OK;
+  const uint32_t got = *c->h_learn_n < HS_LEARN_MAX ? *c->h_learn_n : HS_LEARN_MAX;
+  if (got == 0) return HS_OK;
+  if (!c->d_atables) {
+    HS_TRY(cache_allocate(c));
+    if (!c->cache_enabled) return HS_OK;
+  }
+  const size_t old_n = c->n_keys;
+  size_t n_new = 0;
+  const uint32_t mask = c->slot_mask;
+  for (uint32_t t = 0; t < got && old_n + n_new < c->cache_cap; t++) {
+    const uint8_t *key = c->h_learn_keys + 32 * (size_t)t;
+    uint32_t w[8];
+    memcpy(w, key, 32);
+    uint32_t h = key_hash(w) & mask;
+    bool present = false;
+    while (c->h_slots[h] != HS_NO_KEY) {
+      if (memcmp(c->h_pks.data() + 32 * (size_t)c->h_slots[h], key, 32) == 0) {
+        present = true;
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+    if (present) continue;
+    c->h_slots[h] = (uint32_t)(old_n + n_new);
+    c->h_pks.insert(c->h_pks.end(), key, key + 32);
+    n_new++;
+  }
+  if (n_new == 0) return HS_OK;
+  HS_CUDA(c, cudaMemcpyAsync(c->d_pks + old_n * 32, c->h_pks.data() + old_n * 32, n_new * 32, cudaMemcpyHostToDevice, stream));
+  HS_CUDA(c, cudaMemcpyAsync(c->d_slots, c->h_slots.data(), c->h_slots.size() * 4, cudaMemcpyHostToDevice, stream));
+  size_t threads = n_new * (size_t)c->cp.na * ((1u << (c->cp.wa - 1)) / HS_BUILD_BLOCK);
+  k_build_comb<<<blocks_for(threads), HS_THREADS, 0, stream>>>(c->d_pks + old_n * 32, n_new, 1, c->cp.wa, c->cp.na,
+                                                                c->d_atables + old_n * c->a_table_entries, c->d_key_flags + old_n);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  // h_pks / h_slots are pageable vectors that may reallocate on the next learn: make the uploads finish first
+  HS_CUDA(c, cudaStreamSynchronize(stream));
+  c->n_keys = old_n + n_new;
+  if (c->n_keys >= c->cache_cap) c->cache_enabled = false;  // full: no eviction, the rest stays on the generic path
+  return HS_OK;
+}
+// After the lookup of a pass: park the unknown keys for learn_process().
+static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_lookup, cudaStream_t stream) {
+  if (!c->cache_enabled || c->explicit_committee || c->learn_pending || !L.pk) return HS_OK;
+  if (!c->d_learn_keys) {
+    HS_CUDA(c, cudaMalloc(&c->d_learn_keys, (size_t)HS_LEARN_MAX * 32));
+    HS_CUDA(c, cudaMalloc(&c->d_learn_n, 4));
+    HS_CUDA(c, cudaMallocHost(&c->h_learn_keys, (size_t)HS_LEARN_MAX * 32));
+    HS_CUDA(c, cudaMallocHost(&c->h_learn_n, 4));
+    HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_learn, cudaEventDisableTiming));
+  }
+  k_gather_keys<<<blocks_for(HS_LEARN_MAX, 256), 256, 0, stream>>>(L, n, have_lookup ? (const uint32_t *)c->miss.p : nullptr,
+                                                                     have_lookup ? c->d_miss_count : nullptr, HS_LEARN_MAX, c->d_learn_keys, c->d_learn_n);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  HS_CUDA(c, cudaMemcpyAsync(c->h_learn_n, c->d_learn_n, 4, cudaMemcpyDeviceToHost, stream));
+  HS_CUDA(c, cudaMemcpyAsync(c->h_learn_keys, c->d_learn_keys, (size_t)HS_LEARN_MAX * 32, cudaMemcpyDeviceToHost, stream));
+  HS_CUDA(c, cudaEventRecord(c->ev_learn, stream));
+  c->learn_pending = true;
+  return HS_OK;
+}
+
 // Runs lookup (optional) -> main (committee and/or generic) -> finish on `stream` for a device-resident layout.
 // use_lookup: L.pk is valid and a committee is registered -> resolve indices on the device.
 static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed) {
   if (n == 0) return HS_OK;
+  if (!indexed) HS_TRY(learn_process(c, stream));
   HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
   HS_TRY(ensure(c, c->meta, n));
   main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, 0};
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
-  if (indexed && c->n_keys == 0) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
+  if (indexed && !c->explicit_committee) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (committee) {
     if (!indexed) {
       HS_TRY(ensure(c, c->vidx, n * 4));
@@ -508,6 +662,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
       HS_CUDA(c, cudaGetLastError());
       L.vidx = (const uint32_t *)c->vidx.p;
       O.side_pass = 1;
+      HS_TRY(learn_collect(c, L, n, true, stream));
       // Records whose key is not registered take the generic path over the compacted list.  One generic verify has a
       // ~0.8 ms single-warp latency, so the pass runs on the high-priority side stream CONCURRENTLY with the committee
       // pass (disjoint outputs); its length stays on the device (no host round trip).
@@ -525,6 +680,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     HS_CUDA(c, cudaGetLastError());
     if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_side[1], 0));
   } else {
+    HS_TRY(learn_collect(c, L, n, false, stream));
     k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
@@ -554,18 +710,6 @@ static in_layout layout_rec128(const void *d_recs) {
 
 extern "C" {
 
-static void set_window(comb_params &cp, bool a, int w) {
-  if (a) {
-    cp.wa = w;
-    cp.na = sc_ndigits_rt(w);
-    sc_bias_rt(cp.bias_a, w);
-  } else {
-    cp.wb = w;
-    cp.nb = sc_ndigits_rt(w);
-    sc_bias_rt(cp.bias_b, w);
-  }
-}
-
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   if (!out) return HS_ERR_ARG;
   int wb = (int)(flags & 0xffu);
@@ -593,6 +737,7 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   set_window(c->cp, false, wb);
   set_window(c->cp, true, 12);
   c->wa_forced = (int)((flags >> 8) & 0xffu);
+  c->cache_wanted = c->cache_enabled = !(flags & HS_FLAG_NO_KEY_CACHE) && !(getenv("HS_KEY_CACHE") && getenv("HS_KEY_CACHE")[0] == '0');
   if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * comb_table_entries(wb));
   if (e == cudaSuccess) {
     if (launch_build(c, nullptr, 1, 0, wb, c->cp.nb, c->d_btable, nullptr) != HS_OK) e = cudaGetLastError();
@@ -619,6 +764,11 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_miss_count);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
   for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->xyz, &c->meta, &c->vidx, &c->miss, &c->out}) cudaFree(b->p);
+  cudaFree(c->d_learn_keys);
+  cudaFree(c->d_learn_n);
+  if (c->h_learn_keys) cudaFreeHost(c->h_learn_keys);
+  if (c->h_learn_n) cudaFreeHost(c->h_learn_n);
+  if (c->ev_learn) cudaEventDestroy(c->ev_learn);
   for (int p = 0; p < HS_MAX_PEERS; p++)
     if (c->peer_mapped[p]) cudaIpcCloseMemHandle(c->peer_mapped[p]);
   cudaFree(c->peer_own);
@@ -634,6 +784,7 @@ void hs_ctx_destroy(hs_ctx *c) {
 }
 
 const char *hs_last_error(const hs_ctx *c) { return c ? c->err.c_str() : "null context"; }
+size_t hs_cached_keys(const hs_ctx *c) { return (c && !c->explicit_committee) ? c->n_keys : 0; }
 void hs_window_bits(const hs_ctx *c, int *key_bits, int *base_bits) {
   if (key_bits) *key_bits = (c && c->n_keys) ? c->cp.wa : 0;
   if (base_bits) *base_bits = c ? c->cp.wb : 0;
@@ -655,15 +806,10 @@ int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   HS_CUDA(c, cudaDeviceSynchronize());
-  cudaFree(c->d_pks);
-  cudaFree(c->d_key_flags);
-  cudaFree(c->d_atables);
-  cudaFree(c->d_slots);
-  c->d_pks = nullptr;
-  c->d_key_flags = nullptr;
-  c->d_atables = nullptr;
-  c->d_slots = nullptr;
-  c->n_keys = 0;
+  cache_release(c);
+  c->learn_pending = false;
+  c->explicit_committee = N > 0;   // N == 0 clears the committee and hands key handling back to the cache (if enabled)
+  c->cache_enabled = c->cache_wanted;
   if (N == 0) return HS_OK;
   // host-side hash table (hashing only; first occurrence of a duplicated key wins)
   uint32_t cap = 16;

@@ -35,11 +35,12 @@ def bitmap_to_bools(bitmap, n):
 
 
 class Engine:
-    def __init__(self, device=0, base_window=0, key_window=0):
-        """base_window / key_window: comb window widths in bits (0 = engine defaults: 24 and the widest that fits)."""
+    def __init__(self, device=0, base_window=0, key_window=0, key_cache=True):
+        """base_window / key_window: comb window widths in bits (0 = engine defaults: 24 and the widest that fits).
+        key_cache: learn tables for unregistered keys between calls (include/hs_crypto.h, hs_cached_keys)."""
         self.lib = _lib.load()
         h = ctypes.c_void_p()
-        rc = self.lib.hs_ctx_create(ctypes.byref(h), int(device), (int(base_window) & 0xff) | ((int(key_window) & 0xff) << 8))
+        rc = self.lib.hs_ctx_create(ctypes.byref(h), int(device), (int(base_window) & 0xff) | ((int(key_window) & 0xff) << 8) | (0 if key_cache else 0x10000))
         if rc != 0 or not h:
             raise EngineError("hs_ctx_create(device=%d) failed with status %d (no GPU / CUDA error); there is no CPU fallback" % (device, rc))
         self.h = h
@@ -60,6 +61,10 @@ class Engine:
     def _check(self, rc, what):
         if rc != 0:
             raise EngineError("%s failed: status %d: %s" % (what, rc, self.lib.hs_last_error(self.h).decode()))
+
+    @property
+    def cached_keys(self):
+        return int(self.lib.hs_cached_keys(self.h))
 
     @property
     def window_bits(self):

@@ -24,6 +24,7 @@
 extern "C" {
 #endif
 
+#define HS_FLAG_NO_KEY_CACHE 0x10000u /* hs_ctx_create flag: never learn unregistered keys */
 #define HS_OK 0
 #define HS_ERR_CUDA 1
 #define HS_ERR_ARG 2
@@ -52,11 +53,17 @@ typedef struct {
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
 /* device: CUDA ordinal.  Builds the base-point comb table on the GPU (default window 24 bits = 8.9 GB of HBM).
  * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..24), bits 8-15 = forced per-key window width
- * (8..16; 0 = widest that fits ~62 % of device memory). */
+ * (8..16; 0 = widest that fits ~62 % of device memory); HS_FLAG_NO_KEY_CACHE disables the key cache (also env HS_KEY_CACHE=0). */
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
 const char *hs_last_error(const hs_ctx *ctx);
+/* Key cache: when NO committee is registered, keys that show up in calls carrying key bytes are learned between calls (up to
+ * 4,096 keys, 4.1 MB of table each, allocated on first use): the first sighting of a key takes the generic path, later
+ * ones the table path.  Verdicts are identical either way.  Registering a committee (the robust choice: a flood of one-off
+ * keys can fill the cache, which never evicts) switches learning off; hs_committee_register(.., 0, ..) clears the committee
+ * and re-enables it.  Returns the number of keys currently cached. */
+size_t hs_cached_keys(const hs_ctx *ctx);
 /* Comb window widths in use: per-key tables (0 when no committee is registered) and the base-point table. */
 void hs_window_bits(const hs_ctx *ctx, int *key_bits, int *base_bits);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

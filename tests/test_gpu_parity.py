@@ -394,3 +394,47 @@ def test_verify_qcs_one_pass(engine, oracle):
     assert (engine.verify_qcs(pre, sig, qi, validator_idx=vidx) == want_qc).all()
     assert (engine.verify_qcs(pre, sig, qi, pk=pks[vidx]) == want_qc).all()
     engine.committee_register(np.zeros((0, 32), np.uint8))
+
+
+def test_key_cache_learns_unregistered_keys(oracle):
+    """Nothing registered: the first sighting of a key takes the generic path, the engine builds its table between calls, and
+    later calls take the table path — verdicts identical throughout (honest, corrupted and adversarial keys alike)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hotstuff_b200 import Engine
+    from oracle_api import make_adversarial
+    e = Engine(0, base_window=12)
+    try:
+        w = make_workload(oracle, 6000, n_keys=40, seed=606, corrupt_frac=0.05)
+        recs = to_rec128(w)
+        want = oracle.verify_rec128(recs)
+        assert e.cached_keys == 0
+        for rep in range(4):
+            assert (e.verify_rec128(recs) == want).all(), rep
+        assert e.cached_keys >= 40
+        got = e.verify_var(w["sig"], w["pk"], w["msgs"], w["off"])
+        assert (got == want).all()
+        adv = make_adversarial(oracle, 3000, seed=99)
+        ws, we = oracle.verify_rec128(adv, mode=0), oracle.verify_rec128(adv, mode=1)
+        for rep in range(3):                                   # adversarial keys get cached too; flags must carry over
+            assert (e.verify_rec128(adv, mode=0) == ws).all(), rep
+            assert (e.verify_rec128(adv, mode=1) == we).all(), rep
+        n_cached = e.cached_keys
+        assert n_cached > 40
+        # an explicit committee switches learning off; clearing it switches learning back on with an empty cache
+        e.committee_register(w["pks"])
+        assert e.cached_keys == 0 and (e.verify_rec128(recs) == want).all()
+        e.committee_register(np.zeros((0, 32), np.uint8))
+        for rep in range(3):
+            assert (e.verify_rec128(recs) == want).all()
+        assert e.cached_keys >= 40
+    finally:
+        e.close()
+    e2 = Engine(0, base_window=12, key_cache=False)
+    try:
+        for rep in range(3):
+            assert (e2.verify_rec128(recs) == want).all()
+        assert e2.cached_keys == 0
+    finally:
+        e2.close()
