@@ -544,12 +544,12 @@ static void cache_release(hs_ctx *c) {
   c->h_pks.clear();
   c->h_slots.clear();
 }
-// lazily allocate the store for cache_cap learned keys (12-bit windows: 4.1 MB per key, or narrower if memory is short)
+// lazily allocate the store for cache_cap learned keys (14-bit windows: 14 MB per key, narrower if memory is short)
 static int cache_allocate(hs_ctx *c) {
   size_t free_b = 0, total_b = 0;
   HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   int wa = 8;
-  for (int w : {12, 10, 8}) {
+  for (int w : {14, 12, 10, 8}) {
     wa = w;
     if (c->cache_cap * comb_table_entries(w) * sizeof(ge_niels) <= free_b / 2) break;
   }
