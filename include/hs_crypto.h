@@ -59,7 +59,7 @@ void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
 const char *hs_last_error(const hs_ctx *ctx);
 /* Key cache: when NO committee is registered, keys that show up in calls carrying key bytes are learned between calls (up to
- * 4,096 keys, 4.1 MB of table each, allocated on first use): the first sighting of a key takes the generic path, later
+ * 4,096 keys, 14 MB of table each, allocated on first use): the first sighting of a key takes the generic path, later
  * ones the table path.  Verdicts are identical either way.  Registering a committee (the robust choice: a flood of one-off
  * keys can fill the cache, which never evicts) switches learning off; hs_committee_register(.., 0, ..) clears the committee
  * and re-enables it.  Returns the number of keys currently cached. */
