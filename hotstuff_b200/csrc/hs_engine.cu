@@ -460,6 +460,9 @@ struct hs_ctx {
   uint32_t *d_learn_n = nullptr, *h_learn_n = nullptr;
   cudaEvent_t ev_learn = nullptr;
   bool learn_pending = false;
+  bool cache_full = false;           // no free slot: only the miss RATE is watched (a mostly-missing full cache is reset)
+  size_t learn_records = 0;          // records of the pass whose misses are parked in h_learn_*
+  uint32_t *h_miss_total = nullptr;  // pinned: total misses of that pass
   // multi-GPU peer routing
   peer_route peers{};
   int peer_rank = 0;
@@ -578,6 +581,18 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   if (cudaEventQuery(c->ev_learn) != cudaSuccess) return HS_OK;  // copy still in flight: try again on the next call
   c->learn_pending = false;
   if (!c->cache_enabled || c->explicit_committee) return HS_OK;
+  if (c->cache_full) {
+    // Full cache that no longer matches the traffic (e.g. the validator set rotated): more than half of the last pass missed.
+    // Start over — the next passes relearn the keys that are actually in use.  (No per-key eviction)
+    if (c->learn_records >= 64 && (size_t)*c->h_miss_total * 2 > c->learn_records) {
+      c->n_keys = 0;
+      c->h_pks.clear();
+      std::fill(c->h_slots.begin(), c->h_slots.end(), HS_NO_KEY);
+      HS_CUDA(c, cudaMemsetAsync(c->d_slots, 0xff, c->h_slots.size() * 4, stream));
+      c->cache_full = false;
+    }
+    return HS_OK;
+  }
   const uint32_t got = *c->h_learn_n < HS_LEARN_MAX ? *c->h_learn_n : HS_LEARN_MAX;
   if (got == 0) return HS_OK;
   if (!c->d_atables) {
@@ -616,7 +631,7 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   // h_pks / h_slots are pageable vectors that may reallocate on the next learn: make the uploads finish first
   HS_CUDA(c, cudaStreamSynchronize(stream));
   c->n_keys = old_n + n_new;
-  if (c->n_keys >= c->cache_cap) c->cache_enabled = false;  // full: no eviction, the rest stays on the generic path
+  if (c->n_keys >= c->cache_cap) c->cache_full = true;  // no free slot: unknown keys stay on the generic path until a reset
   return HS_OK;
 }
 // After the lookup of a pass: park the unknown keys for learn_process().
@@ -627,7 +642,16 @@ static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_look
     HS_CUDA(c, cudaMalloc(&c->d_learn_n, 4));
     HS_CUDA(c, cudaMallocHost(&c->h_learn_keys, (size_t)HS_LEARN_MAX * 32));
     HS_CUDA(c, cudaMallocHost(&c->h_learn_n, 4));
+    HS_CUDA(c, cudaMallocHost(&c->h_miss_total, 4));
     HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_learn, cudaEventDisableTiming));
+  }
+  c->learn_records = n;
+  if (c->cache_full) {  // only watch the miss rate
+    if (!have_lookup) return HS_OK;
+    HS_CUDA(c, cudaMemcpyAsync(c->h_miss_total, c->d_miss_count, 4, cudaMemcpyDeviceToHost, stream));
+    HS_CUDA(c, cudaEventRecord(c->ev_learn, stream));
+    c->learn_pending = true;
+    return HS_OK;
   }
   k_gather_keys<<<blocks_for(HS_LEARN_MAX, 256), 256, 0, stream>>>(L, n, have_lookup ? (const uint32_t *)c->miss.p : nullptr,
                                                                      have_lookup ? c->d_miss_count : nullptr, HS_LEARN_MAX, c->d_learn_keys, c->d_learn_n);
@@ -768,6 +792,7 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_learn_n);
   if (c->h_learn_keys) cudaFreeHost(c->h_learn_keys);
   if (c->h_learn_n) cudaFreeHost(c->h_learn_n);
+  if (c->h_miss_total) cudaFreeHost(c->h_miss_total);
   if (c->ev_learn) cudaEventDestroy(c->ev_learn);
   for (int p = 0; p < HS_MAX_PEERS; p++)
     if (c->peer_mapped[p]) cudaIpcCloseMemHandle(c->peer_mapped[p]);
@@ -808,6 +833,7 @@ int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out
   HS_CUDA(c, cudaDeviceSynchronize());
   cache_release(c);
   c->learn_pending = false;
+  c->cache_full = false;
   c->explicit_committee = N > 0;   // N == 0 clears the committee and hands key handling back to the cache (if enabled)
   c->cache_enabled = c->cache_wanted;
   if (N == 0) return HS_OK;

@@ -60,8 +60,9 @@ void hs_ctx_destroy(hs_ctx *ctx);
 const char *hs_last_error(const hs_ctx *ctx);
 /* Key cache: when NO committee is registered, keys that show up in calls carrying key bytes are learned between calls (up to
  * 4,096 keys, 14 MB of table each, allocated on first use): the first sighting of a key takes the generic path, later
- * ones the table path.  Verdicts are identical either way.  Registering a committee (the robust choice: a flood of one-off
- * keys can fill the cache, which never evicts) switches learning off; hs_committee_register(.., 0, ..) clears the committee
+ * ones the table path.  Verdicts are identical either way.  A full cache that misses on more than half of a pass is reset
+ * and relearns (validator-set rotation); there is no per-key eviction, so registering the committee remains the robust
+ * choice against floods of one-off keys.  Registering switches learning off; hs_committee_register(.., 0, ..) clears the committee
  * and re-enables it.  Returns the number of keys currently cached. */
 size_t hs_cached_keys(const hs_ctx *ctx);
 /* Comb window widths in use: per-key tables (0 when no committee is registered) and the base-point table. */

@@ -438,3 +438,28 @@ def test_key_cache_learns_unregistered_keys(oracle):
         assert e2.cached_keys == 0
     finally:
         e2.close()
+
+
+def test_key_cache_resets_when_the_key_set_rotates(oracle, monkeypatch):
+    """A full cache that misses on most of a pass (validator-set rotation) is cleared and relearns."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hotstuff_b200 import Engine
+    e = Engine(0, base_window=12, key_window=8)
+    try:
+        cap = 4096
+        a = make_workload(oracle, 2 * cap, n_keys=cap, seed=1)          # exactly fills the cache
+        ra, wa_ = to_rec128(a), None
+        wa_ = oracle.verify_rec128(ra)
+        for _ in range(3):
+            assert (e.verify_rec128(ra) == wa_).all()
+        assert e.cached_keys == cap
+        b = make_workload(oracle, 3000, n_keys=50, seed=2)               # a different key set
+        rb = to_rec128(b)
+        wb = oracle.verify_rec128(rb)
+        for _ in range(5):
+            assert (e.verify_rec128(rb) == wb).all()
+        assert 50 <= e.cached_keys < cap                                 # reset happened, the new set was learned
+    finally:
+        e.close()
