@@ -553,6 +553,7 @@ static int cache_allocate(hs_ctx *c) {
   HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   int wa = 8;
   for (int w : {14, 12, 10, 8}) {
+    if (c->wa_forced && w != c->wa_forced && w != 8) continue;
     wa = w;
     if (c->cache_cap * comb_table_entries(w) * sizeof(ge_niels) <= free_b / 2) break;
   }
