@@ -1178,10 +1178,14 @@ int hs_verify_msgs(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint3
     HS_TRY(ensure(c, c->vidx, chunk_cap * 4));
     HS_TRY(ensure(c, c->miss, chunk_cap * 4));
   }
-  size_t nchunks = (n + CH - 1) / CH;
-  for (size_t j = 0; j < nchunks; j++) {
+  // Ramp: a short first chunk gets the kernels going while the first full-size copy is still in flight (the first copy and the last
+  // chunk's kernels are the only un-overlapped parts of the pipeline).
+  const size_t first = (n > 2 * CH) ? ((CH / 4) & ~(size_t)31) : 0;  // bitmap words must not straddle chunks
+  size_t lo = 0;
+  for (size_t j = 0; lo < n; j++) {
     const int b = (int)(j & 1);
-    const size_t lo = j * CH, cnt = (n - lo < CH) ? (n - lo) : CH;
+    const size_t want = (j == 0 && first) ? first : CH;
+    const size_t cnt = (n - lo < want) ? (n - lo) : want;
     uint8_t *d = (uint8_t *)c->in[b].p;
     const size_t o_sig = 0, o_key = cnt * 64, o_msg = o_key + ((cnt * key_bytes + 15) & ~(size_t)15);
     if (j >= 2) HS_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_done[b], 0));  // staging buffer b is free again
@@ -1194,6 +1198,7 @@ int hs_verify_msgs(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint3
     HS_TRY(hs_verify_msgs_dev(c, d + o_sig, vidx ? nullptr : d + o_key, vidx ? d + o_key : nullptr, d + o_msg, msg_len, cnt, mode,
                               c->digest[b].p, (uint32_t *)c->out.p + lo / 32, c->stream));
     HS_CUDA(c, cudaEventRecord(c->ev_done[b], c->stream));
+    lo += cnt;
   }
   return finish_bitmap(c, n, out_bitmap);
 }
