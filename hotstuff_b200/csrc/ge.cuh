@@ -214,7 +214,8 @@ HS_HD uint32_t ge_decompress(ge_ext &p, const uint32_t (&enc)[8]) {
 // non-canonical y (y + p, only possible for y < 19) before use, and ignores the sign bit when x = 0, so
 // [8]P == identity  <=>  (enc mod 2^255) in {0, 1, p-1, p, p+1, y8, p-y8}  (every one of these decompresses, with
 // either sign bit).  Equivalent to dalek is_small_order() = mul_by_cofactor().is_identity() for decompressible input;
-// tests/test_small_order.py checks the equivalence against the oracle's [8]P computation.
+// tests/test_oracle_pins.py::test_small_order_equivalence and tests/test_hostemu.py::test_decompress_and_small_order check the
+// equivalence against the oracle's [8]P computation.
 HS_HD uint32_t ge_enc_is_small_order(const uint32_t (&enc)[8]) {
   const uint32_t top = enc[7] & 0x7fffffffu;
   // y = 0 / 1 (canonical): limbs 1..7 zero, limb0 in {0,1}
