@@ -145,3 +145,31 @@ def test_multithreaded_batch_matches_single(oracle):
     b = oracle.verify_rec128(recs, nthreads=8)
     assert (a == b).all() and (~a).sum() >= 1
     assert (a[~w["corrupted"]]).all()
+
+
+def test_adversarial_differential_against_libsodium(oracle):
+    """Independent pin over the adversarial classes: for CANONICAL A and R encodings (y < p) libsodium's verify has the same accept set
+    as dalek's verify_strict — S must be canonical, small-order A and R are rejected, the equation is cofactorless — so the oracle's
+    strict verdict must equal libsodium's on every such record of the randomised adversarial generator (mixed-order keys and nonces,
+    S + l, torsion points, random encodings, bit flips).  (Non-canonical encodings are where the two libraries are KNOWN to differ:
+    libsodium rejects them, dalek reduces them; those records are skipped here and covered by the golden matrix.)"""
+    import nacl.bindings
+    from oracle_api import P, make_adversarial
+    recs = make_adversarial(oracle, 6000, seed=31337)
+    strict = oracle.verify_rec128(recs, mode=0)
+    compared = accepted = 0
+    for r, s in zip(recs, strict):
+        sig, pk, m = r[:64].tobytes(), r[64:96].tobytes(), r[96:].tobytes()
+        y_a = int.from_bytes(pk, "little") & (2**255 - 1)
+        y_r = int.from_bytes(sig[:32], "little") & (2**255 - 1)
+        if y_a >= P or y_r >= P:
+            continue
+        try:
+            nacl.bindings.crypto_sign_open(sig + m, pk)
+            sodium = True
+        except Exception:
+            sodium = False
+        assert sodium == bool(s), (sig.hex(), pk.hex(), m.hex())
+        compared += 1
+        accepted += sodium
+    assert compared > 5000 and 500 < accepted < compared - 500
