@@ -173,3 +173,35 @@ def test_adversarial_differential_against_libsodium(oracle):
         compared += 1
         accepted += sodium
     assert compared > 5000 and 500 < accepted < compared - 500
+
+
+def test_adversarial_differential_against_openssl(oracle):
+    """Independent pin of the batch-equation semantics (HSO_EQ_OK, the per-vote condition of verify_batch): OpenSSL checks S < l,
+    decompresses A, recomputes R' = [S]B - [k]A without any small-order rule and compares R' with the signature's R bytes.  For
+    canonically encoded A and R (excluding the 'x = 0 with sign bit' spellings, which OpenSSL's byte comparison rejects and dalek's
+    point comparison accepts) that is exactly the cofactorless equation, so OpenSSL's verdict must equal the oracle's EQ verdict."""
+    from cryptography.exceptions import InvalidSignature
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PublicKey
+    from oracle_api import P, make_adversarial
+    recs = make_adversarial(oracle, 6000, seed=4242)
+    eq = oracle.verify_rec128(recs, mode=1)
+    strict = oracle.verify_rec128(recs, mode=0)
+    compared = differs_from_strict = 0
+    for r, e, s in zip(recs, eq, strict):
+        sig, pk, m = r[:64].tobytes(), r[64:96].tobytes(), r[96:].tobytes()
+        bad_spelling = False
+        for enc in (pk, sig[:32]):
+            y = int.from_bytes(enc, "little") & (2**255 - 1)
+            if y >= P or (y in (1, P - 1) and enc[31] >> 7):
+                bad_spelling = True
+        if bad_spelling:
+            continue
+        try:
+            Ed25519PublicKey.from_public_bytes(pk).verify(sig, m)
+            ossl = True
+        except (InvalidSignature, ValueError):
+            ossl = False
+        assert ossl == bool(e), (sig.hex(), pk.hex(), m.hex())
+        compared += 1
+        differs_from_strict += bool(e) != bool(s)
+    assert compared > 5000 and differs_from_strict > 100   # the set exercises the strict / batch-eq gap
