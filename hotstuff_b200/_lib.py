@@ -23,6 +23,8 @@ SIGNATURES = {
     "hs_verify_batch_shared_msg": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_int), c_void_p]),
     "hs_verify_qcs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "hs_committee_register": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hs_committee_update": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "hs_set_table_budget": (c_int, [c_void_p, c_size_t]),
     "hs_verify_committee": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_u32, c_void_p]),
     "hs_digest32_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hs_verify_rec128_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),

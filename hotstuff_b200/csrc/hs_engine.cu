@@ -54,25 +54,30 @@ __device__ __forceinline__ void load32(uint32_t (&w)[8], const uint8_t *p) {
   for (int i = 0; i < 8; i++) w[i] = __ldg(s + i);
 }
 
-// A warp loads its 32 packed 128-byte records (4 KB) with fully coalesced 16-byte accesses, parks them in shared
-// memory under an XOR swizzle, and every lane then reads back its own record conflict-free.
-__device__ __forceinline__ void warp_load_rec128(uint32_t (&sig_r)[8], uint32_t (&sig_s)[8], uint32_t (&pk)[8], uint32_t (&msg)[8],
-                                                 const uint4 *__restrict__ recs, size_t n, size_t warp_first, uint4 *smem_warp) {
+// A warp loads 32 rows of 128 bytes (row r at base + (warp_first + r) * stride, 16-byte aligned) with fully coalesced
+// 16-byte accesses, parks them in shared memory under an XOR swizzle, and every lane then reads back its own row
+// conflict-free.  Rows past n read as zeros.  Every lane of the warp must call it.
+__device__ __forceinline__ void warp_stage_rows128(uint4 (&q)[8], const uint8_t *__restrict__ base, size_t stride, size_t n, size_t warp_first,
+                                                   uint4 *smem_warp) {
   const int lane = threadIdx.x & 31;
-  const uint4 *src = recs + warp_first * 8;  // 8 x 16 B per record
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     int c = j * 32 + lane;  // chunk index inside the warp's 4 KB
     int rec = c >> 3, part = c & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (warp_first + rec < n) v = __ldg(src + c);
+    if (warp_first + rec < n) v = __ldg(reinterpret_cast<const uint4 *>(base + (warp_first + rec) * stride) + part);
     smem_warp[rec * 8 + (part ^ (rec & 7))] = v;
   }
   __syncwarp();
-  uint4 q[8];
 #pragma unroll
   for (int part = 0; part < 8; part++) q[part] = smem_warp[lane * 8 + (part ^ (lane & 7))];
   __syncwarp();
+}
+// packed hs_rec128 records: sig.R | sig.S | pk | msg
+__device__ __forceinline__ void warp_load_rec128(uint32_t (&sig_r)[8], uint32_t (&sig_s)[8], uint32_t (&pk)[8], uint32_t (&msg)[8],
+                                                 const uint4 *__restrict__ recs, size_t n, size_t warp_first, uint4 *smem_warp) {
+  uint4 q[8];
+  warp_stage_rows128(q, reinterpret_cast<const uint8_t *>(recs), 128, n, warp_first, smem_warp);
   sig_r[0] = q[0].x; sig_r[1] = q[0].y; sig_r[2] = q[0].z; sig_r[3] = q[0].w; sig_r[4] = q[1].x; sig_r[5] = q[1].y; sig_r[6] = q[1].z; sig_r[7] = q[1].w;
   sig_s[0] = q[2].x; sig_s[1] = q[2].y; sig_s[2] = q[2].z; sig_s[3] = q[2].w; sig_s[4] = q[3].x; sig_s[5] = q[3].y; sig_s[6] = q[3].z; sig_s[7] = q[3].w;
   pk[0] = q[4].x; pk[1] = q[4].y; pk[2] = q[4].z; pk[3] = q[4].w; pk[4] = q[5].x; pk[5] = q[5].y; pk[6] = q[5].z; pk[7] = q[5].w;
@@ -256,28 +261,52 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : 3)
 // peer's result buffer over NVLink (P2P stores through CUDA-IPC mapped pointers), then a release flag per (writer, reader)
 // pair tells the reader the shard has landed.  Payload is n/8 bytes per rank: latency, not bandwidth.
 #define HS_MAX_PEERS 16
+// Result buffer of one rank (cudaMalloc'd, exported over CUDA IPC):
+//   [2][total_words]  the global bitmap, double-buffered by epoch parity: a fast rank's epoch e+1 words land in the OTHER
+//                     half, so a slower rank that is still reading epoch e never sees them (r1's single buffer had a
+//                     write-after-read hazard); a rank can run at most one epoch ahead, because finishing epoch e+1
+//                     needs every peer's epoch e+1 flag, which a peer publishes only after its own epoch-e readers ran
+//                     (stream order: consume epoch e's bitmap before enqueueing the verify of epoch e+1)
+//   [HS_MAX_PEERS]    flags[w] = last epoch whose words from writer w have landed here (release/acquire, system scope)
+//   [0] timeout flag, [1] finish-kernel block counter
 struct peer_route {
-  uint32_t *buf[HS_MAX_PEERS];  // buf[p] = base of rank p's result buffer as mapped in THIS process (words, then flags)
+  uint32_t *buf[HS_MAX_PEERS];  // buf[p] = base of rank p's result buffer as mapped in THIS process
   int n;                        // world size (0 = route disabled: plain local bitmap)
+  int my_rank;
+  uint32_t epoch;
+  size_t total_words;           // words of the global bitmap; rank p owns [p * total_words / n, (p + 1) * total_words / n)
   size_t word_offset;           // this rank's first word in the global bitmap
 };
-__global__ void k_peer_signal(peer_route P, size_t total_words, int my_rank, uint32_t epoch) {
+#define HS_PEER_FLAGS(P) ((P).total_words * 2)
+#define HS_PEER_CTRL(P) ((P).total_words * 2 + HS_MAX_PEERS)
+// Executed by ONE block after all of this rank's words of the epoch are stored (and fenced): thread p publishes this rank's
+// flag in rank p's buffer, then waits for rank p's flag here.  A peer that never shows up is an error, not a hang: the spin
+// is bounded, the sticky timeout flag is raised and that peer's shard is cleared (every verdict reads "reject").
+__device__ __forceinline__ void peer_signal_and_wait(const peer_route &P) {
   const int p = threadIdx.x;
   if (p >= P.n) return;
-  __threadfence_system();  // the finish kernel's peer stores (previous launch on this stream) are ordered before the flag
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.buf[p] + total_words + my_rank), "r"(epoch) : "memory");
-}
-__global__ void k_peer_wait(const uint32_t *flags, int n, uint32_t epoch, uint32_t *timeout_flag) {
-  const int p = threadIdx.x;
-  if (p >= n) return;
+  uint32_t *own = P.buf[P.my_rank];
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.buf[p] + HS_PEER_FLAGS(P) + P.my_rank), "r"(P.epoch) : "memory");
   uint32_t v = 0;
-  for (long long spin = 0; spin < (1ll << 24); spin++) {  // bounded (~5 s): a missing peer becomes an error, never a hang
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
-    if ((int32_t)(v - epoch) >= 0) return;
+  bool ok = false;
+  for (long long spin = 0; spin < (1ll << 24); spin++) {  // bounded (~5 s)
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(own + HS_PEER_FLAGS(P) + p) : "memory");
+    if ((int32_t)(v - P.epoch) >= 0) {
+      ok = true;
+      break;
+    }
     __nanosleep(200);
   }
-  *timeout_flag = 1;
+  if (!ok) {
+    own[HS_PEER_CTRL(P)] = 1;
+    const size_t per = P.total_words / P.n;
+    uint32_t *w = own + (P.epoch & 1u) * P.total_words + (size_t)p * per;
+    for (size_t k = 0; k < per; k++) w[k] = 0;
+  }
 }
+// shard without records: nothing to verify, but the peers still wait for this rank's flag
+__global__ void k_peer_sync_only(const peer_route P) { peer_signal_and_wait(P); }
 
 // ------------------------------------------------------------------------------------------------ phase 2: finish
 __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
@@ -289,7 +318,8 @@ __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
 // field inversion per 64 records is executed (by warp 0, lane l inverting the product of threads 4l..4l+3) instead of one
 // per thread: phase A prefix products of the thread's 16 Z's; phase B the block-level inversion through shared memory;
 // phase C back-substitution + affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into
-// one bitmap word, which goes to the local bitmap or — armed by hs_peer_next — straight into every peer's buffer.
+// one bitmap word, which goes to the local bitmap or — armed by hs_peer_next — straight into every peer's buffer, after
+// which the last block of the grid exchanges the epoch flags with the peers (no separate signal / wait launches).
 __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_t n, const fe *__restrict__ xyz, const uint8_t *__restrict__ meta,
                                                                uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out, const peer_route P) {
   __shared__ fe tot[HS_THREADS];
@@ -361,7 +391,21 @@ __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_
       bitmap[t >> 1] = word;
     } else {
 #pragma unroll 1
-      for (int p = 0; p < P.n; p++) P.buf[p][P.word_offset + (t >> 1)] = word;  // fused all-gather: one NVLink store per peer
+      const size_t at = (P.epoch & 1u) * P.total_words + P.word_offset + (t >> 1);
+      for (int p = 0; p < P.n; p++) P.buf[p][at] = word;  // fused all-gather: one NVLink store per peer
+    }
+  }
+  if (P.n) {
+    // the last block to get here publishes the epoch flag to every peer and waits for theirs: the exchange costs no launch
+    __shared__ int is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(P.buf[P.my_rank] + HS_PEER_CTRL(P) + 1, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+      peer_signal_and_wait(P);
+      __syncthreads();
+      if (threadIdx.x == 0) P.buf[P.my_rank][HS_PEER_CTRL(P) + 1] = 0;
     }
   }
 }
@@ -396,7 +440,7 @@ __global__ void __launch_bounds__(HS_THREADS) k_build_comb(const uint8_t *__rest
     P = Q;
   }
   fe prod[HS_BUILD_BLOCK];
-  comb_build_block(tables + p * ((size_t)n_windows << (W - 1)), P, W, w, b * HS_BUILD_BLOCK, HS_BUILD_BLOCK, prod);
+  comb_build_block(tables + p * ((size_t)n_windows * comb_window_stride(W)), P, W, w, b * HS_BUILD_BLOCK, HS_BUILD_BLOCK, prod);
 }
 
 // ------------------------------------------------------------------------------------------------ Digest kernels
@@ -409,6 +453,45 @@ __global__ void __launch_bounds__(HS_THREADS) k_digest32(const uint8_t *__restri
   const uint8_t *m = off ? data + off[i] : data + i * fixed_len;
   const uint64_t len = off ? off[i + 1] - off[i] : fixed_len;
   sha512_prefix_msg(h, pre, 0, m, len);
+  uint4 *dst = reinterpret_cast<uint4 *>(out + i * 8);
+  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// Fixed-size, 16-byte aligned messages (the transaction / payload shape of BASELINE config[1]): every full 128-byte block is
+// fetched by the warp with coalesced 16-byte loads through shared memory (a per-thread 8-byte walk touches 32 sectors per
+// load instruction), and when the length is a multiple of 128 the padding-only last block runs without its message
+// schedule (sha512_compress_kw).  Other lengths finish through the generic reader.
+__global__ void __launch_bounds__(HS_THREADS) k_digest32_fixed(const uint8_t *__restrict__ data, uint64_t len, size_t n, uint32_t *__restrict__ out,
+                                                                const sha512_kw padkw, int pad_is_const) {
+  __shared__ __align__(16) uint4 stage[HS_THREADS / 32][256];
+  const size_t i = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
+  const size_t warp_first = i & ~(size_t)31;
+  if (warp_first >= n) return;  // whole warp past the end
+  sha512_state s;
+  sha512_init(s);
+  const uint64_t nfull = len >> 7;
+#pragma unroll 1
+  for (uint64_t b = 0; b < nfull; b++) {
+    uint4 q[8];
+    warp_stage_rows128(q, data + b * 128, len, n, warp_first, stage[threadIdx.x >> 5]);
+    uint64_t w[16];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      w[2 * k] = be64_from_le32(q[k].x, q[k].y);
+      w[2 * k + 1] = be64_from_le32(q[k].z, q[k].w);
+    }
+    sha512_compress(s, w);
+  }
+  if (i >= n) return;
+  if (pad_is_const) {
+    sha512_compress_kw(s, padkw);
+  } else {
+    const uint64_t pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sha512_absorb_blocks(s, pre, 0, data + i * len, len, nfull, sha512_nblocks(len));
+  }
+  uint32_t h[16];
+  sha512_output_words(s, h);
   uint4 *dst = reinterpret_cast<uint4 *>(out + i * 8);
   dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
@@ -454,8 +537,11 @@ struct hs_ctx {
   bool explicit_committee = false;   // hs_committee_register was called with keys: the set is fixed, nothing is learned
   bool cache_wanted = true, cache_enabled = true;
   size_t cache_cap = 4096;           // keys
-  std::vector<uint8_t> h_pks;        // host mirrors of d_pks / d_slots while the cache is in use
+  std::vector<uint8_t> h_pks;        // host mirrors of d_pks / d_slots (key cache and hs_committee_update)
   std::vector<uint32_t> h_slots;
+  std::vector<uint8_t> h_key_live;   // explicit committee: 1 = slot holds a live validator, 0 = removed (free for reuse)
+  size_t table_budget = 0;           // bytes the per-key tables may use (0 = ~62 % of the device)
+  size_t key_capacity = 0;           // explicit committee: table slots allocated (>= n_keys; spare slots serve hs_committee_update)
   uint8_t *d_learn_keys = nullptr, *h_learn_keys = nullptr;
   uint32_t *d_learn_n = nullptr, *h_learn_n = nullptr;
   cudaEvent_t ev_learn = nullptr;
@@ -467,17 +553,19 @@ struct hs_ctx {
   peer_route peers{};
   int peer_rank = 0;
   size_t peer_total_words = 0;
-  uint32_t *peer_own = nullptr;       // cudaMalloc'd: [total_words][HS_MAX_PEERS flags][timeout flag]
+  uint32_t *peer_own = nullptr;       // cudaMalloc'd: [2][total_words][HS_MAX_PEERS flags][timeout flag, block counter]
   void *peer_mapped[HS_MAX_PEERS] = {};
   bool peer_armed = false;
   uint32_t peer_epoch = 0;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
+  std::mutex err_mu;                  // guards err only: fail() is also reached from argument checks taken before `mu`
   std::string err = "ok";
 };
 
 static int fail(hs_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
   if (c) {
+    std::lock_guard<std::mutex> g(c->err_mu);
     c->err = what;
     if (e != cudaSuccess) {
       c->err += ": ";
@@ -546,18 +634,22 @@ static void cache_release(hs_ctx *c) {
   c->n_keys = 0;
   c->h_pks.clear();
   c->h_slots.clear();
+  c->h_key_live.clear();
+  c->key_capacity = 0;
 }
 // lazily allocate the store for cache_cap learned keys (14-bit windows: 14 MB per key, narrower if memory is short)
 static int cache_allocate(hs_ctx *c) {
   size_t free_b = 0, total_b = 0;
   HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t lim = free_b / 2;
+  if (c->table_budget && c->table_budget < lim) lim = c->table_budget;
   int wa = 8;
   for (int w : {14, 12, 10, 8}) {
     if (c->wa_forced && w != c->wa_forced && w != 8) continue;
     wa = w;
-    if (c->cache_cap * comb_table_entries(w) * sizeof(ge_niels) <= free_b / 2) break;
+    if (c->cache_cap * comb_table_entries(w) * sizeof(ge_niels) <= lim) break;
   }
-  if (c->cache_cap * comb_table_entries(wa) * sizeof(ge_niels) > free_b / 2 || sc_ndigits_rt(wa) + c->cp.nb > HS_MAX_DIGITS) {
+  if (c->cache_cap * comb_table_entries(wa) * sizeof(ge_niels) > lim || sc_ndigits_rt(wa) + c->cp.nb > HS_MAX_DIGITS) {
     c->cache_enabled = false;  // not enough memory: stay on the generic path
     return HS_OK;
   }
@@ -668,14 +760,23 @@ static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_look
 // Runs lookup (optional) -> main (committee and/or generic) -> finish on `stream` for a device-resident layout.
 // use_lookup: L.pk is valid and a committee is registered -> resolve indices on the device.
 static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed) {
-  if (n == 0) return HS_OK;
+  if (n == 0) {
+    if (c->peer_armed) {  // an empty shard still owes its peers the epoch flag
+      c->peer_armed = false;
+      k_peer_sync_only<<<1, HS_MAX_PEERS, 0, stream>>>(c->peers);
+      c->launches++;
+      HS_CUDA(c, cudaGetLastError());
+    }
+    return HS_OK;
+  }
+  if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (!indexed) HS_TRY(learn_process(c, stream));
   HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
   HS_TRY(ensure(c, c->meta, n));
   main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, 0};
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
-  if (indexed && !c->explicit_committee) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
+  if (!committee && !L.pk) return fail(c, HS_ERR_ARG, "verify without keys");
   if (committee) {
     if (!indexed) {
       HS_TRY(ensure(c, c->vidx, n * 4));
@@ -719,12 +820,23 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, nullptr, P);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
-  if (P.n) {
-    k_peer_signal<<<1, HS_MAX_PEERS, 0, stream>>>(P, c->peer_total_words, c->peer_rank, c->peer_epoch);
-    k_peer_wait<<<1, HS_MAX_PEERS, 0, stream>>>(c->peer_own + c->peer_total_words, P.n, c->peer_epoch, c->peer_own + c->peer_total_words + HS_MAX_PEERS);
-    c->launches += 2;
-    HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+
+// Digest of n fixed-size messages: staged/coalesced kernel when every message starts 16-byte aligned and has at least one
+// full block, the generic per-thread reader otherwise.
+static int launch_digest_fixed(hs_ctx *c, const uint8_t *d_msgs, size_t msg_len, size_t n, uint32_t *d_out, cudaStream_t stream) {
+  if (msg_len >= 128 && (msg_len & 15) == 0 && (reinterpret_cast<uintptr_t>(d_msgs) & 15) == 0) {
+    sha512_kw kw;
+    const int pad_is_const = (msg_len & 127) == 0;
+    if (pad_is_const) sha512_pad_schedule(kw, msg_len);
+    else memset(&kw, 0, sizeof(kw));
+    k_digest32_fixed<<<blocks_for(n), HS_THREADS, 0, stream>>>(d_msgs, msg_len, n, d_out, kw, pad_is_const);
+  } else {
+    k_digest32<<<blocks_for(n), HS_THREADS, 0, stream>>>(d_msgs, nullptr, msg_len, n, d_out);
   }
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
   return HS_OK;
 }
 
@@ -762,6 +874,7 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   set_window(c->cp, false, wb);
   set_window(c->cp, true, 12);
   c->wa_forced = (int)((flags >> 8) & 0xffu);
+  if (const char *b = getenv("HS_TABLE_BUDGET_MB")) c->table_budget = (size_t)strtoull(b, nullptr, 10) << 20;
   c->cache_wanted = c->cache_enabled = !(flags & HS_FLAG_NO_KEY_CACHE) && !(getenv("HS_KEY_CACHE") && getenv("HS_KEY_CACHE")[0] == '0');
   if (e == cudaSuccess) e = cudaMalloc(&c->d_btable, sizeof(ge_niels) * comb_table_entries(wb));
   if (e == cudaSuccess) {
@@ -827,21 +940,30 @@ void hs_host_free(void *p) {
 }
 
 // ---- committee registration
-int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out_valid_bitmap) {
-  if (!c || (N && !pks) || N >= HS_NO_KEY) return fail(c, HS_ERR_ARG, "hs_committee_register: bad argument");
-  std::lock_guard<std::mutex> g(c->mu);
+static int committee_register_locked(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out_valid_bitmap) {
   HS_CUDA(c, cudaSetDevice(c->device));
   HS_CUDA(c, cudaDeviceSynchronize());
   cache_release(c);
   c->learn_pending = false;
   c->cache_full = false;
-  c->explicit_committee = N > 0;   // N == 0 clears the committee and hands key handling back to the cache (if enabled)
+  c->explicit_committee = false;   // set only once the new tables are complete: a failed registration leaves NO committee
   c->cache_enabled = c->cache_wanted;
-  if (N == 0) return HS_OK;
+  if (N == 0) return HS_OK;        // clears the committee and hands key handling back to the cache (if enabled)
   // host-side hash table (hashing only; first occurrence of a duplicated key wins)
   uint32_t cap = 16;
-  while (cap < 2 * N) cap <<= 1;
-  std::vector<uint32_t> slots(cap, HS_NO_KEY);
+  std::vector<uint32_t> slots;
+  // widest per-key window whose tables fit in the budget: ~62 % of the device by default (B200: 16 bits up to ~2.2 k keys,
+  // 15 up to ~4.2 k, 14 up to ~7.6 k, 12 up to ~26 k), or HS_TABLE_BUDGET_MB / hs_set_table_budget for a shared device
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = total_b / 100 * 62;
+  if (c->table_budget) budget = c->table_budget;
+  if (budget > free_b - free_b / 8) budget = free_b - free_b / 8;
+  // spare slots (1/16 of the set, at least 16) let hs_committee_update add validators without rebuilding anything
+  const size_t capk = N + (N / 16 > 16 ? N / 16 : 16);
+  while (cap < 2 * capk) cap <<= 1;
+  slots.clear();
+  slots.assign(cap, HS_NO_KEY);
   for (size_t i = 0; i < N; i++) {
     uint32_t w[8];
     memcpy(w, pks + 32 * i, 32);
@@ -856,38 +978,131 @@ int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out
     }
     if (!dup) slots[h] = (uint32_t)i;
   }
-  HS_CUDA(c, cudaMalloc(&c->d_pks, N * 32));
-  HS_CUDA(c, cudaMalloc(&c->d_key_flags, N));
-  HS_CUDA(c, cudaMalloc(&c->d_slots, (size_t)cap * 4));
-  // widest per-key window whose tables fit in ~62 % of the device (B200: 16 bits up to ~2.2 k keys, 15 up to ~4.2 k, 14 up to ~7.6 k, 12 up to ~26 k)
-  size_t free_b = 0, total_b = 0;
-  HS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = total_b / 100 * 62;
-  if (budget > free_b - free_b / 8) budget = free_b - free_b / 8;
   int wa = 8;
   for (int w : {16, 15, 14, 13, 12, 11, 10, 9, 8}) {
     if (c->wa_forced && w != c->wa_forced) continue;
     wa = w;
-    if (N * comb_table_entries(w) * sizeof(ge_niels) <= budget) break;
+    if (capk * comb_table_entries(w) * sizeof(ge_niels) <= budget) break;
   }
   if (sc_ndigits_rt(wa) + c->cp.nb > HS_MAX_DIGITS) return fail(c, HS_ERR_ARG, "window combination exceeds HS_MAX_DIGITS");
+  cudaError_t e = cudaMalloc(&c->d_pks, capk * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_key_flags, capk);
+  if (e == cudaSuccess) e = cudaMemset(c->d_key_flags, 0, capk);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_slots, (size_t)cap * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_atables, capk * sizeof(ge_niels) * comb_table_entries(wa));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cache_release(c);
+    return fail(c, HS_ERR_NOMEM, "committee tables do not fit in device memory", e);
+  }
   set_window(c->cp, true, wa);
   c->a_table_entries = comb_table_entries(wa);
-  cudaError_t e = cudaMalloc(&c->d_atables, N * sizeof(ge_niels) * c->a_table_entries);
-  if (e != cudaSuccess) return fail(c, HS_ERR_NOMEM, "committee tables do not fit in device memory", e);
-  HS_CUDA(c, cudaMemcpyAsync(c->d_pks, pks, N * 32, cudaMemcpyHostToDevice, c->stream));
-  HS_CUDA(c, cudaMemcpyAsync(c->d_slots, slots.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, c->stream));
-  HS_TRY(launch_build(c, c->d_pks, N, 1, wa, c->cp.na, c->d_atables, c->d_key_flags));
-  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  int rc = HS_OK;
+  e = cudaMemcpyAsync(c->d_pks, pks, N * 32, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_slots, slots.data(), (size_t)cap * 4, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) rc = launch_build(c, c->d_pks, N, 1, wa, c->cp.na, c->d_atables, c->d_key_flags);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaStreamSynchronize(c->stream);
+  std::vector<uint8_t> fl(N);
+  if (e == cudaSuccess && rc == HS_OK) e = cudaMemcpy(fl.data(), c->d_key_flags, N, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess || rc != HS_OK) {
+    cache_release(c);
+    return rc != HS_OK ? rc : fail(c, HS_ERR_CUDA, "committee registration", e);
+  }
   c->slot_mask = cap - 1;
   c->n_keys = N;
+  c->key_capacity = capk;
+  c->explicit_committee = true;
+  c->h_pks.assign(pks, pks + N * 32);  // host mirror: hs_committee_update edits the set incrementally
+  c->h_slots = slots;
+  c->h_key_live.assign(N, 1);
   if (out_valid_bitmap) {
-    std::vector<uint8_t> fl(N);
-    HS_CUDA(c, cudaMemcpy(fl.data(), c->d_key_flags, N, cudaMemcpyDeviceToHost));
     for (size_t w = 0; w < (N + 31) / 32; w++) out_valid_bitmap[w] = 0;
     for (size_t i = 0; i < N; i++)
       if (fl[i] & 1) out_valid_bitmap[i >> 5] |= 1u << (i & 31);
   }
+  return HS_OK;
+}
+int hs_committee_register(hs_ctx *c, const uint8_t *pks, size_t N, uint32_t *out_valid_bitmap) {
+  if (!c || (N && !pks) || N >= HS_NO_KEY) return fail(c, HS_ERR_ARG, "hs_committee_register: bad argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  return committee_register_locked(c, pks, N, out_valid_bitmap);
+}
+
+// Incremental epoch change (consensus/src/config.rs Committee: a few validators join / leave): removed indices stop
+// verifying (flag cleared, hash slot dropped), added keys take a free slot — a removed one or a spare — and only THEIR tables
+// are built (~0.25 ms per key); every other validator keeps its index and its table.
+int hs_committee_update(hs_ctx *c, const uint8_t *add_pks, size_t n_add, const uint32_t *remove_idx, size_t n_remove, uint32_t *out_add_idx) {
+  if (!c || (n_add && (!add_pks || !out_add_idx)) || (n_remove && !remove_idx)) return fail(c, HS_ERR_ARG, "hs_committee_update: bad argument");
+  std::lock_guard<std::mutex> g(c->mu);
+  if (!c->explicit_committee) return fail(c, HS_ERR_ARG, "hs_committee_update: no committee registered");
+  HS_CUDA(c, cudaSetDevice(c->device));
+  HS_CUDA(c, cudaDeviceSynchronize());  // epoch boundary: nothing of the old set may be in flight
+  for (size_t i = 0; i < n_remove; i++)
+    if (remove_idx[i] >= c->n_keys) return fail(c, HS_ERR_ARG, "hs_committee_update: remove index out of range");
+  for (size_t i = 0; i < n_remove; i++) {
+    c->h_key_live[remove_idx[i]] = 0;
+    HS_CUDA(c, cudaMemsetAsync(c->d_key_flags + remove_idx[i], 0, 1, c->stream));
+  }
+  auto find = [&](const uint8_t *key) -> uint32_t {
+    uint32_t w[8];
+    memcpy(w, key, 32);
+    uint32_t h = key_hash(w) & c->slot_mask;
+    while (c->h_slots[h] != HS_NO_KEY) {
+      const uint32_t idx = c->h_slots[h];
+      if (c->h_key_live[idx] && memcmp(c->h_pks.data() + 32 * (size_t)idx, key, 32) == 0) return idx;
+      h = (h + 1) & c->slot_mask;
+    }
+    return HS_NO_KEY;
+  };
+  size_t next_free = 0;
+  std::vector<uint32_t> added;
+  for (size_t i = 0; i < n_add; i++) {
+    const uint8_t *key = add_pks + 32 * i;
+    uint32_t idx = find(key);
+    for (uint32_t a : added)  // the same key twice in one call
+      if (idx == HS_NO_KEY && memcmp(c->h_pks.data() + 32 * (size_t)a, key, 32) == 0) idx = a;
+    if (idx == HS_NO_KEY) {
+      while (next_free < c->n_keys && c->h_key_live[next_free]) next_free++;
+      if (next_free < c->n_keys) idx = (uint32_t)next_free;
+      else if (c->n_keys < c->key_capacity) {
+        idx = (uint32_t)c->n_keys++;
+        c->h_key_live.push_back(0);
+        c->h_pks.resize(c->n_keys * 32);
+      } else return fail(c, HS_ERR_NOMEM, "hs_committee_update: no free table slot (re-register the committee)");
+      memcpy(c->h_pks.data() + 32 * (size_t)idx, key, 32);
+      c->h_key_live[idx] = 1;
+      HS_CUDA(c, cudaMemcpyAsync(c->d_pks + 32 * (size_t)idx, key, 32, cudaMemcpyHostToDevice, c->stream));
+      HS_TRY(launch_build(c, c->d_pks + 32 * (size_t)idx, 1, 1, c->cp.wa, c->cp.na, c->d_atables + (size_t)idx * c->a_table_entries, c->d_key_flags + idx));
+      added.push_back(idx);
+    }
+    out_add_idx[i] = idx;
+  }
+  // rebuild the open-addressing table from the live keys (deletions leave no tombstones) and publish it
+  std::fill(c->h_slots.begin(), c->h_slots.end(), HS_NO_KEY);
+  for (size_t i = 0; i < c->n_keys; i++) {
+    if (!c->h_key_live[i]) continue;
+    uint32_t w[8];
+    memcpy(w, c->h_pks.data() + 32 * i, 32);
+    uint32_t h = key_hash(w) & c->slot_mask;
+    bool dup = false;
+    while (c->h_slots[h] != HS_NO_KEY) {
+      if (memcmp(c->h_pks.data() + 32 * (size_t)c->h_slots[h], c->h_pks.data() + 32 * i, 32) == 0) {
+        dup = true;
+        break;
+      }
+      h = (h + 1) & c->slot_mask;
+    }
+    if (!dup) c->h_slots[h] = (uint32_t)i;
+  }
+  HS_CUDA(c, cudaMemcpyAsync(c->d_slots, c->h_slots.data(), c->h_slots.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+/* Upper bound (bytes) for the per-key tables of the NEXT registration / key-cache allocation; 0 = default (~62 % of the device). */
+int hs_set_table_budget(hs_ctx *c, size_t bytes) {
+  if (!c) return HS_ERR_ARG;
+  std::lock_guard<std::mutex> g(c->mu);
+  c->table_budget = bytes;
   return HS_OK;
 }
 
@@ -930,9 +1145,7 @@ int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const voi
   HS_CUDA(c, cudaSetDevice(c->device));
   // Digest(msg_i) in its own kernel: fusing it into k_verify_main was measured SLOWER on B200 (4.53 vs 4.13 ms per 2^20: the
   // SHA phase then runs at the curve kernel's 128-register occupancy and the two phases do not overlap across pipes in practice).
-  k_digest32<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_msgs, nullptr, msg_len, n, (uint32_t *)d_digests);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
+  HS_TRY(launch_digest_fixed(c, (const uint8_t *)d_msgs, msg_len, n, (uint32_t *)d_digests, (cudaStream_t)stream));
   in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, (const uint32_t *)d_vidx, (const uint8_t *)d_digests, 32, nullptr, nullptr, 32, 0};
   return run_verify(c, L, n, mode, (uint32_t *)d_bitmap, (cudaStream_t)stream, d_vidx != nullptr);
 }
@@ -979,11 +1192,12 @@ int hs_verify_qcs(hs_ctx *c, const uint8_t *preimages, size_t n_qc, const uint8_
 
 // ---- multi-GPU peer routing (one process per GPU; handles are exchanged by the host, e.g. torch.distributed.all_gather_object)
 int hs_peer_setup(hs_ctx *c, int rank, int world, size_t total_words, uint8_t handle_out[64]) {
-  if (!c || world < 1 || world > HS_MAX_PEERS || rank < 0 || rank >= world || !handle_out) return fail(c, HS_ERR_ARG, "hs_peer_setup: bad argument");
+  if (!c || world < 1 || world > HS_MAX_PEERS || rank < 0 || rank >= world || !handle_out || total_words % (size_t)world)
+    return fail(c, HS_ERR_ARG, "hs_peer_setup: bad argument (total_words must be a multiple of world)");
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   if (c->peer_own) return fail(c, HS_ERR_ARG, "hs_peer_setup: already set up");
-  const size_t bytes = (total_words + HS_MAX_PEERS + 16) * 4;
+  const size_t bytes = (2 * total_words + HS_MAX_PEERS + 16) * 4;
   HS_CUDA(c, cudaMalloc(&c->peer_own, bytes));
   HS_CUDA(c, cudaMemset(c->peer_own, 0, bytes));
   cudaIpcMemHandle_t h;
@@ -994,6 +1208,8 @@ int hs_peer_setup(hs_ctx *c, int rank, int world, size_t total_words, uint8_t ha
   c->peer_total_words = total_words;
   c->peers = peer_route{};
   c->peers.n = world;
+  c->peers.my_rank = rank;
+  c->peers.total_words = total_words;
   c->peers.buf[rank] = c->peer_own;
   return HS_OK;
 }
@@ -1012,24 +1228,35 @@ int hs_peer_open(hs_ctx *c, int peer_rank, const uint8_t handle[64]) {
 /* Arms the NEXT `_dev` verify call on this context: its bitmap goes to every rank's buffer at word_offset (fused all-gather). */
 int hs_peer_next(hs_ctx *c, size_t word_offset, uint32_t epoch) {
   if (!c || !c->peer_own) return fail(c, HS_ERR_ARG, "hs_peer_next: peers not set up");
+  std::lock_guard<std::mutex> g(c->mu);
   for (int p = 0; p < c->peers.n; p++)
     if (!c->peers.buf[p]) return fail(c, HS_ERR_ARG, "hs_peer_next: a peer buffer is not mapped");
+  if (c->peer_epoch != 0 && epoch != c->peer_epoch + 1) return fail(c, HS_ERR_ARG, "hs_peer_next: epochs must increase by one");
+  if (word_offset >= c->peer_total_words && c->peer_total_words) return fail(c, HS_ERR_ARG, "hs_peer_next: word_offset out of range");
   c->peers.word_offset = word_offset;
+  c->peers.epoch = epoch;
   c->peer_epoch = epoch;
   c->peer_armed = true;
   return HS_OK;
 }
-/* Device pointer of this rank's copy of the full bitmap, and whether a peer wait ever timed out. */
-void *hs_peer_bitmap(hs_ctx *c) { return c ? (void *)c->peer_own : nullptr; }
+/* Device pointer of this rank's copy of the full bitmap of the most recently armed epoch, and whether a peer wait ever timed out. */
+void *hs_peer_bitmap(hs_ctx *c) { return (c && c->peer_own) ? (void *)(c->peer_own + (size_t)(c->peer_epoch & 1u) * c->peer_total_words) : nullptr; }
 int hs_peer_timed_out(hs_ctx *c) {
   if (!c || !c->peer_own) return 0;
   uint32_t v = 0;
   cudaSetDevice(c->device);
-  cudaMemcpy(&v, c->peer_own + c->peer_total_words + HS_MAX_PEERS, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(&v, c->peer_own + 2 * c->peer_total_words + HS_MAX_PEERS, 4, cudaMemcpyDeviceToHost);
   return (int)v;
 }
 
 // ---- host-pointer entry points
+// off[0] == 0 and off[i] <= off[i+1]: a decreasing offset would make a length wrap to ~2^64 on the device
+static bool offsets_ok(const uint64_t *off, size_t n) {
+  if (off[0] != 0) return false;
+  for (size_t i = 0; i < n; i++)
+    if (off[i] > off[i + 1]) return false;
+  return true;
+}
 static int finish_bitmap(hs_ctx *c, size_t n, uint32_t *out_bitmap) {
   size_t words = (n + 31) / 32;
   HS_CUDA(c, cudaMemcpyAsync(out_bitmap, c->out.p, words * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1056,6 +1283,7 @@ int hs_verify_var(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint8_
                   uint32_t *out_bitmap) {
   if (!c || mode > 1 || (n && (!sig || !pk || !off || !out_bitmap))) return fail(c, HS_ERR_ARG, "hs_verify_var: bad argument");
   if (n == 0) return HS_OK;
+  if (!offsets_ok(off, n)) return fail(c, HS_ERR_ARG, "hs_verify_var: offsets must start at 0 and be non-decreasing");
   if (off[n] && !msgs) return fail(c, HS_ERR_ARG, "hs_verify_var: null msgs");
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
@@ -1131,6 +1359,7 @@ int hs_verify_committee(hs_ctx *c, const uint32_t *vidx, const uint8_t *sig, con
 int hs_digest32_batch(hs_ctx *c, const uint8_t *data, const uint64_t *off, size_t n, uint8_t *out) {
   if (!c || (n && (!off || !out))) return fail(c, HS_ERR_ARG, "hs_digest32_batch: bad argument");
   if (n == 0) return HS_OK;
+  if (!offsets_ok(off, n)) return fail(c, HS_ERR_ARG, "hs_digest32_batch: offsets must start at 0 and be non-decreasing");
   if (off[n] && !data) return fail(c, HS_ERR_ARG, "hs_digest32_batch: null data");
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));

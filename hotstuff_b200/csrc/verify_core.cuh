@@ -38,7 +38,11 @@ struct comb_params {
   int wb, nb;  // base-point table
   uint32_t bias_a[9], bias_b[9];
 };
-HS_HD size_t comb_table_entries(int w) { return (size_t)sc_ndigits_rt(w) << (w - 1); }
+// Table layout: window i occupies entries [i * (H + 1), (i + 1) * (H + 1)), H = 2^(w-1); entry 0 of a window is the
+// identity (1, 1, 0) and entry m is m * 2^(w i) * P, so a digit of magnitude 0 .. H indexes the table directly — no
+// "digit == 0" branch or select in the hot loop (one extra 96-byte entry per window).
+HS_HD size_t comb_window_stride(int w) { return ((size_t)1 << (w - 1)) + 1; }
+HS_HD size_t comb_table_entries(int w) { return (size_t)sc_ndigits_rt(w) * comb_window_stride(w); }
 #define HS_MAX_DIGITS 64  // >= na + nb for every supported (wa, wb) pair (wa, wb >= 8)
 
 // most-significant-digit-first stream over a radix-16 recoding (generic-key window method); W * ndigits must be 256
@@ -99,62 +103,89 @@ HS_HD void ge_comb_accumulate_rt(ge_ext &acc, const ge_niels *table, const int32
     uint32_t neg = (uint32_t)(d < 0);
     int mag = d < 0 ? -d : d;
     ge_niels q;
-    if (mag == 0) ge_niels_identity(q);
-    else niels_load(q, table + ((size_t)i << (w - 1)) + (mag - 1));
+    niels_load(q, table + (size_t)i * comb_window_stride(w) + mag);
     ge_madd_signed(acc, acc, q, neg);
   }
 }
 
 // acc = sum over the A windows of digit * 2^(wa i) * (-A)  +  sum over the B windows of digit * 2^(wb i) * B.
 // dig[0 .. na) are k's digits, dig[na .. na+nb) are S's.  ONE loop body (one copy of the mixed addition in the
-// instruction cache) with the table entry of iteration i+1 fetched while iteration i's addition executes.
-#ifndef HS_PREFETCH
-#define HS_PREFETCH 1
-#endif
-HS_HD void ge_comb_ab(ge_ext &acc, const ge_niels *atab, const ge_niels *btab, const int32_t *dig, int stride, const comb_params &cp) {
-  const int NA = cp.na, NT = cp.na + cp.nb;
-  ge_identity(acc);
-#if !HS_PREFETCH
+// instruction cache).  Shape of an iteration (keep non-multiply work off the integer-multiply pipe):
+//   * the sign of the digit is applied AT LOAD TIME: -q = (ymx, ypx, -xy2d), so the two halves of the entry are simply
+//     fetched into each other's registers (pointer selection, no fe_select), and the sign of xy2d is absorbed by choosing
+//     which of F / G feeds X3 and Y3 (Z3 = F G is symmetric);
+//   * the entry of iteration i+1 is fetched into the SAME registers right after the three multiplications that consume
+//     entry i — the remaining four multiplications cover the latency, and there is no q = q_next register copy;
+//   * digit 0 indexes the window's identity entry: no branch, no select.
+struct niels_signed {  // table entry with the digit's sign applied to the first two coordinates
+  fe m0, m1, xy2d;     // m0 multiplies (Y - X), m1 multiplies (Y + X)
+};
+HS_HD void niels_load_signed(niels_signed &q, const ge_niels *entry, uint32_t neg, bool stream) {
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-  for (int j = 0; j < NT; j++) {
-    int d = dig[j * stride];
-    uint32_t neg = (uint32_t)(d < 0);
-    int mag = d < 0 ? -d : d;
-    ge_niels q;
-    if (mag == 0) ge_niels_identity(q);
-    else if (j < NA) niels_load_stream(q, atab + ((size_t)j << (cp.wa - 1)) + (mag - 1));
-    else niels_load(q, btab + ((size_t)(j - NA) << (cp.wb - 1)) + (mag - 1));
-    ge_madd_signed(acc, acc, q, neg);
+  const uint4 *s = reinterpret_cast<const uint4 *>(entry);
+  const uint4 *p0 = s + (neg ? 0 : 2), *p1 = s + (neg ? 2 : 0);  // ypx at +0, ymx at +32 bytes
+  uint4 a, b, c, d, e, f;
+  if (stream) {
+    a = __ldcs(p0); b = __ldcs(p0 + 1); c = __ldcs(p1); d = __ldcs(p1 + 1); e = __ldcs(s + 4); f = __ldcs(s + 5);
+  } else {
+    a = __ldg(p0); b = __ldg(p0 + 1); c = __ldg(p1); d = __ldg(p1 + 1); e = __ldg(s + 4); f = __ldg(s + 5);
   }
-  return;
+  q.m0.v[0] = a.x; q.m0.v[1] = a.y; q.m0.v[2] = a.z; q.m0.v[3] = a.w; q.m0.v[4] = b.x; q.m0.v[5] = b.y; q.m0.v[6] = b.z; q.m0.v[7] = b.w;
+  q.m1.v[0] = c.x; q.m1.v[1] = c.y; q.m1.v[2] = c.z; q.m1.v[3] = c.w; q.m1.v[4] = d.x; q.m1.v[5] = d.y; q.m1.v[6] = d.z; q.m1.v[7] = d.w;
+  q.xy2d.v[0] = e.x; q.xy2d.v[1] = e.y; q.xy2d.v[2] = e.z; q.xy2d.v[3] = e.w; q.xy2d.v[4] = f.x; q.xy2d.v[5] = f.y; q.xy2d.v[6] = f.z; q.xy2d.v[7] = f.w;
+#else
+  (void)stream;
+  q.m0 = neg ? entry->ypx : entry->ymx;
+  q.m1 = neg ? entry->ymx : entry->ypx;
+  q.xy2d = entry->xy2d;
 #endif
-  ge_niels qn;
-  uint32_t negn;
+}
+HS_HD const ge_niels *comb_entry(const ge_niels *atab, const ge_niels *btab, const int32_t *dig, int stride, int j, const comb_params &cp,
+                                 uint32_t &neg, bool &is_a) {
+  const int d = dig[j * stride];
+  neg = (uint32_t)(d < 0);
+  const int mag = d < 0 ? -d : d;
+  is_a = j < cp.na;
+  return is_a ? atab + (size_t)j * comb_window_stride(cp.wa) + mag : btab + (size_t)(j - cp.na) * comb_window_stride(cp.wb) + mag;
+}
+HS_HD void ge_comb_ab(ge_ext &acc, const ge_niels *atab, const ge_niels *btab, const int32_t *dig, int stride, const comb_params &cp) {
+  const int NT = cp.na + cp.nb;
+  ge_identity(acc);
+  niels_signed q;
+  uint32_t neg, negn = 0;
+  bool is_a;
   {
-    int d = dig[0];
-    negn = (uint32_t)(d < 0);
-    int mag = d < 0 ? -d : d;
-    if (mag == 0) ge_niels_identity(qn);
-    else niels_load_stream(qn, atab + (mag - 1));
+    const ge_niels *e = comb_entry(atab, btab, dig, stride, 0, cp, neg, is_a);
+    niels_load_signed(q, e, neg, is_a);
   }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
   for (int i = 0; i < NT; i++) {
-    ge_niels q = qn;
-    const uint32_t neg = negn;
-    if (i + 1 < NT) {
-      const int j = i + 1;
-      int d = dig[j * stride];
-      negn = (uint32_t)(d < 0);
-      int mag = d < 0 ? -d : d;
-      if (mag == 0) ge_niels_identity(qn);
-      else if (j < NA) niels_load_stream(qn, atab + ((size_t)j << (cp.wa - 1)) + (mag - 1));
-      else niels_load(qn, btab + ((size_t)(j - NA) << (cp.wb - 1)) + (mag - 1));
+    fe a, b, t, dd;
+    fe_sub(t, acc.Y, acc.X);
+    fe_mul(a, t, q.m0);
+    fe_add(t, acc.Y, acc.X);
+    fe_mul(b, t, q.m1);
+    fe_mul(t, acc.T, q.xy2d);
+    if (i + 1 < NT) {  // entry i is consumed: fetch entry i+1 into the same registers
+      const ge_niels *e = comb_entry(atab, btab, dig, stride, i + 1, cp, negn, is_a);
+      if (is_a) niels_load_signed(q, e, negn, true);   // per-key tables stream through L2 (evict-first)
+      else niels_load_signed(q, e, negn, false);
     }
-    ge_madd_signed(acc, acc, q, neg);
+    fe_add(dd, acc.Z, acc.Z);
+    fe E, H, F, G, P, Q;
+    fe_sub(E, b, a);
+    fe_add(H, b, a);
+    fe_sub(F, dd, t);
+    fe_add(G, dd, t);
+    fe_select(P, F, G, neg);  // -q negates t, i.e. swaps F and G
+    fe_select(Q, G, F, neg);
+    fe_mul(acc.X, E, P);
+    fe_mul(acc.Y, Q, H);
+    fe_mul(acc.Z, F, G);
+    fe_mul(acc.T, E, H);
+    neg = negn;
   }
 }
 
@@ -247,8 +278,8 @@ HS_HD uint32_t verify_flags_from(const fe &X, const fe &Y, const fe &zinv, const
 }
 
 // ---- table construction (runs on the GPU at context creation / committee registration; also under host emu)
-// Fills entries [first, first+count) of window `win` of P's comb table: entry e (0-based) = (e+1) * 2^(W win) * P as an
-// affine Niels point.  The forward pass parks (X, Y, Z) in the destination slots and the running product of the Z's in
+// Fills entries [first + 1, first + 1 + count) of window `win` of P's comb table: entry m = m * 2^(W win) * P as an
+// affine Niels point (the call with first == 0 also writes the window's identity entry 0).  The forward pass parks (X, Y, Z) in the destination slots and the running product of the Z's in
 // `prod` (count entries of scratch); one inversion then serves the whole block (Montgomery's trick).
 HS_HD void comb_build_block(ge_niels *table, const ge_ext &P, int W, int win, int first, int count, fe *prod) {
   ge_ext base = P;
@@ -269,7 +300,8 @@ HS_HD void comb_build_block(ge_niels *table, const ge_ext &P, int W, int win, in
     ge_dbl(m, m);
     if ((mult >> b) & 1) ge_add_cached(m, m, cb);
   }
-  ge_niels *slot = table + ((size_t)win << (W - 1)) + first;
+  ge_niels *slot = table + (size_t)win * comb_window_stride(W) + 1 + first;  // entry 0 of the window is the identity
+  if (first == 0) ge_niels_identity(slot[-1]);
   fe run;
   fe_set1(run);
 #if defined(__CUDA_ARCH__)

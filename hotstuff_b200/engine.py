@@ -142,6 +142,18 @@ class Engine:
         self.n_keys = n
         return bitmap_to_bools(bm, n)
 
+    def committee_update(self, add=None, remove=None):
+        """Incremental epoch change (hs_committee_update): returns the indices assigned to the added keys."""
+        add = np.zeros((0, 32), np.uint8) if add is None else _u8(add, 32).reshape(-1, 32)
+        rem = np.zeros(0, np.uint32) if remove is None else np.ascontiguousarray(remove, dtype=np.uint32)
+        out = np.zeros(max(1, add.shape[0]), dtype=np.uint32)
+        self._check(self.lib.hs_committee_update(self.h, _ptr(add) if add.shape[0] else None, add.shape[0], _ptr(rem) if rem.shape[0] else None,
+                                                 rem.shape[0], _ptr(out)), "hs_committee_update")
+        return out[: add.shape[0]]
+
+    def set_table_budget(self, nbytes):
+        self._check(self.lib.hs_set_table_budget(self.h, int(nbytes)), "hs_set_table_budget")
+
     def verify_committee(self, validator_idx, sig, digests, msg_idx=None, mode=MODE_STRICT):
         vidx = np.ascontiguousarray(validator_idx, dtype=np.uint32)
         sig = _u8(sig, 64).reshape(-1, 64)

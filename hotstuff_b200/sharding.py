@@ -72,16 +72,23 @@ class PeerAllGather:
         if int(flag.item()) == 0:
             raise RuntimeError("peer buffers could not be set up on every rank: " + engine.lib.hs_last_error(engine.h).decode())
         self.epoch = 0
-        ptr = engine.lib.hs_peer_bitmap(engine.h)
-        # zero-copy torch view of this rank's full-bitmap buffer
+        ptr = engine.lib.hs_peer_bitmap(engine.h)   # epoch 0 -> first half of the double buffer
+        # zero-copy torch view of this rank's result buffer: [2][total_words], indexed by epoch parity
         class _Arr:
-            __cuda_array_interface__ = {"shape": (self.total_words,), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
-        self.full = torch.as_tensor(_Arr(), device=torch.device("cuda", engine.device))
+            __cuda_array_interface__ = {"shape": (2, self.total_words), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+        self._both = torch.as_tensor(_Arr(), device=torch.device("cuda", engine.device))
 
     def arm(self):
         """Call right before the engine's `_dev` verify of this rank's shard."""
         self.epoch += 1
         self.e._check(self.e.lib.hs_peer_next(self.e.h, self.rank * self.per_words, self.epoch), "hs_peer_next")
 
+    @property
+    def full(self):
+        """All total_words of the most recently armed epoch (this rank's copy of every rank's verdicts)."""
+        return self._both[self.epoch & 1]
+
     def bitmap(self):
-        return self.full[: (self.n + 31) // 32] if self.world * self.per_words * 32 >= self.n else self.full
+        """The (n+31)//32 meaningful words.  Consume it (same stream) before arming the next epoch + 1 verify: the buffer is
+        double-buffered by epoch parity, so no cross-rank barrier is needed between epochs."""
+        return self.full[: (self.n + 31) // 32]

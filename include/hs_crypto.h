@@ -102,6 +102,16 @@ int hs_verify_qcs(hs_ctx *ctx, const uint8_t *preimages, size_t n_qc, const uint
 /* Decompresses every key and builds its comb table in HBM (window 16 bits: 48 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
 int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
+/* Incremental epoch change: validators remove_idx[] stop verifying (their indices become free), keys add_pks[] take a free
+ * or spare slot (registration reserves N/16, at least 16, spare slots) and only their tables are built; out_add_idx[i]
+ * receives the index of add_pks[i] (an already-registered key returns its existing index).  Everyone else keeps index and
+ * table.  HS_ERR_NOMEM when no slot is free: re-register.  Requires a registered committee. */
+int hs_committee_update(hs_ctx *ctx, const uint8_t *add_pks /* n_add x 32 */, size_t n_add, const uint32_t *remove_idx, size_t n_remove,
+                        uint32_t *out_add_idx);
+/* Memory budget (bytes) for the per-key tables of the NEXT registration / key-cache allocation (0 = default, ~62 % of the
+ * device; also env HS_TABLE_BUDGET_MB at context creation).  The engine picks the widest window that fits: e.g. 4,096 keys in
+ * 18 GB -> 12-bit windows.  Lets the engine sit beside another tenant on the same GPU. */
+int hs_set_table_budget(hs_ctx *ctx, size_t bytes);
 /* Vote i is (validator_idx[i], sig[i]) over digests[msg_idx[i]].  msg_idx may be NULL when n_msgs == 1. */
 int hs_verify_committee(hs_ctx *ctx, const uint32_t *validator_idx, const uint8_t *sig /* n x 64 */, const uint32_t *msg_idx,
                         const uint8_t *digests /* n_msgs x 32 */, size_t n_msgs, size_t n, uint32_t mode, uint32_t *out_bitmap);
@@ -133,7 +143,11 @@ int hs_verify_msgs_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk_or_null,
  * exchanges handles (e.g. torch.distributed.all_gather_object) and opens every peer's.  hs_peer_next() then arms the next
  * `_dev` verify call: its finish kernel stores each bitmap word it produces directly into EVERY rank's buffer at
  * word_offset (P2P stores over NVLink), signals the peers and waits for theirs — after the call (stream order) the buffer
- * returned by hs_peer_bitmap() holds every rank's verdicts for that epoch.  Epochs must increase by one per armed call. */
+ * returned by hs_peer_bitmap() holds every rank's verdicts for that epoch.  Epochs must increase by one per armed call.
+ * The buffer is double-buffered by epoch parity (hs_peer_bitmap() follows the most recently armed epoch): consume epoch e's
+ * bitmap on the same stream before enqueueing the verify of epoch e+1 and no barrier between ranks is needed.  The flag
+ * exchange runs inside the finish kernel (no extra launches).  total_words must be world x (words per rank); a peer that
+ * never signals makes hs_peer_timed_out() return 1 and its shard read as all-rejected. */
 int hs_peer_setup(hs_ctx *ctx, int rank, int world, size_t total_words, uint8_t handle_out[64]);
 int hs_peer_open(hs_ctx *ctx, int peer_rank, const uint8_t handle[64]);
 int hs_peer_next(hs_ctx *ctx, size_t word_offset, uint32_t epoch);

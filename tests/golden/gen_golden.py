@@ -275,6 +275,140 @@ for ln in (0, 1, 46, 47, 48, 49, 63, 64, 111, 112, 174, 175, 176, 177, 512):
         mb[ln // 2] ^= 0x10
         add("var_len_%d_corrupt" % ln, O.sign(seed0, m), pk0, bytes(mb), "varlen", independent=False)
 
+# ------------------------------------------------------------------------------------------------ 4. ed25519-speccheck classes
+# The twelve case classes of Chalkias, Garillot, Nikolaenko, "Taming the many EdDSAs" (SSR 2020), Table 6 / the
+# ed25519-speccheck suite (github.com/novifinancial/ed25519-speccheck, README results table).  The published verdicts for
+# ed25519-dalek are
+#     Dalek  (PublicKey::verify)        : V V V V X X X X X X X V      (cases 0..11)
+#     Dalek strict (verify_strict)      : X X X V X X X X X X X X
+# The suite's hex vectors are not available offline, so each CLASS is re-constructed here from its definition (same
+# algebraic structure: which of A / R are small / mixed order, whether S is canonical, whether a non-canonical encoding is
+# reduced before hashing) and the oracle's verdict is REQUIRED to equal the published dalek verdict of that class:
+# `Signature::verify` (crypto/src/lib.rs:203) is verify_strict, so `strict` must follow the second row.  The first row is
+# dalek's non-strict verify, which compares R'.compress() with the R bytes; the per-signature condition of verify_batch
+# (our batch_eq) decompresses R instead, so it coincides with row one except on class 9 (non-canonical R), where it accepts.
+SPEC_DALEK_VERIFY = [True, True, True, True, False, False, False, False, False, False, False, True]
+SPEC_DALEK_STRICT = [False, False, False, True, False, False, False, False, False, False, False, False]
+srnd = random.Random(1212)
+T8 = torsion_encs[10]            # order 8
+T4_nc = le(P)                    # y = 0 (order 4) under its non-canonical alias y = p
+T4 = le(0)
+ID_nc = le(P + 1)                # identity under the alias y = p + 1
+
+
+def hram(Rb, Ab, m):
+    return O.sc_reduce64(hashlib.sha512(Rb + Ab + m).digest())
+
+
+def spec_add(cls, sig, pk, m, note):
+    v = add("speccheck_class_%d" % cls, sig, pk, m, "speccheck", note)
+    v["speccheck_class"] = cls
+    v["published_dalek_verify"] = SPEC_DALEK_VERIFY[cls]
+    v["published_dalek_strict"] = SPEC_DALEK_STRICT[cls]
+    v["citation"] = "Chalkias-Garillot-Nikolaenko 2020, Table 6; ed25519-speccheck README (rows Dalek / Dalek strict), case %d" % cls
+    assert v["strict"] == SPEC_DALEK_STRICT[cls], (cls, v)
+    want_eq = SPEC_DALEK_VERIFY[cls] if cls != 9 else True
+    assert v["batch_eq"] == want_eq, (cls, v)
+    return v
+
+
+def search(build, want_eq, tag):
+    """build(m) -> (sig, pk); first message whose cofactorless equation verdict (hashing the bytes as given) is want_eq."""
+    for ctr in range(4000):
+        m = hashlib.sha512(b"speccheck" + tag + ctr.to_bytes(2, "little")).digest()[:32]
+        sig, pk = build(m)
+        if bool(O.flags(sig, pk, m) & EQ_OK) == want_eq:
+            return sig, pk, m
+    raise AssertionError("no message found for " + tag.decode())
+
+
+def honest_r(m):
+    return int.from_bytes(hashlib.sha512(prefix + m).digest(), "little") % L_ORDER
+
+
+A_mix = O.point_add(pk0, T8)
+# 0: S = 0, small A, small R, equation holds
+sig, pk, m = search(lambda m: (T4 + bytes(32), T8), True, b"c0")
+spec_add(0, sig, pk, m, "S = 0, small-order A and R; equation holds")
+# 1: 0 < S < l, small A, mixed R = [r]B + T', S = r, [k]A + T' = O
+sig, pk, m = search(lambda m: (O.point_add(O.scalarmult(honest_r(m), B_enc), torsion_encs[11]) + le(honest_r(m)), T8), True, b"c1")
+spec_add(1, sig, pk, m, "small-order A, mixed-order R; equation holds")
+# 2: mixed A, small R, S = k a
+sig, pk, m = search(lambda m: (T8 + le(hram(T8, A_mix, m) * a_scalar % L_ORDER), A_mix), True, b"c2")
+spec_add(2, sig, pk, m, "mixed-order A, small-order R; equation holds")
+
+
+def mixed_both(m):
+    r = honest_r(m)
+    Rm = O.point_add(O.scalarmult(r, B_enc), torsion_encs[11])
+    return Rm + le((r + hram(Rm, A_mix, m) * a_scalar) % L_ORDER), A_mix
+
+
+# 3 / 4: mixed A, mixed R: cofactorless equation holds / holds only after multiplying by the cofactor
+sig, pk, m = search(mixed_both, True, b"c3")
+spec_add(3, sig, pk, m, "mixed-order A and R; cofactorless equation holds (the only class verify_strict accepts)")
+sig, pk, m = search(mixed_both, False, b"c4")
+spec_add(4, sig, pk, m, "mixed-order A and R; only the cofactored equation holds")
+
+
+def mixed_a_only(m):
+    r = honest_r(m)
+    Rm = O.scalarmult(r, B_enc)
+    return Rm + le((r + hram(Rm, A_mix, m) * a_scalar) % L_ORDER), A_mix
+
+
+# 5: mixed A, prime-order R, torsion defect [k]T != O
+sig, pk, m = search(mixed_a_only, False, b"c5")
+spec_add(5, sig, pk, m, "mixed-order A, prime-order R; cofactorless equation fails")
+# 6 / 7: non-canonical S on an otherwise honest signature: S + l (top three bits still clear) and S + 15 l (beyond them)
+m6 = hashlib.sha512(b"speccheck c6").digest()[:32]
+s6 = O.sign(seed0, m6)
+S6 = int.from_bytes(s6[32:], "little")
+assert S6 + L_ORDER < 2**253
+spec_add(6, s6[:32] + le(S6 + L_ORDER), pk0, m6, "S + l: non-canonical, top three bits clear")
+spec_add(7, s6[:32] + le(S6 + 15 * L_ORDER), pk0, m6, "S + 15 l: non-canonical, high bits set")
+
+
+# 8 / 9: non-canonical small-order R (identity as y = p + 1), mixed A, S = k a with k hashed over the REDUCED (8) or the
+# GIVEN (9) encoding of R
+def nc_R(reduced):
+    def build(m):
+        k = hram(le(1) if reduced else ID_nc, A_mix, m)
+        return ID_nc + le(k * a_scalar % L_ORDER), A_mix
+    return build
+
+
+def search_nc(build, hash_holds, tag):
+    # the signer's equation holds when [k]T = O for ITS k; dalek hashes the bytes as given
+    for ctr in range(4000):
+        m = hashlib.sha512(b"speccheck" + tag + ctr.to_bytes(2, "little")).digest()[:32]
+        sig, pk = build(m)
+        if hash_holds(sig, pk, m):
+            return sig, pk, m
+    raise AssertionError(tag)
+
+
+sig, pk, m = search_nc(nc_R(True), lambda s_, p_, m_: hram(le(1), p_, m_) % 8 == 0 and not (O.flags(s_, p_, m_) & EQ_OK), b"c8")
+spec_add(8, sig, pk, m, "non-canonical small-order R; signer hashed the reduced encoding (dalek hashes the bytes as given: reject)")
+sig, pk, m = search_nc(nc_R(False), lambda s_, p_, m_: bool(O.flags(s_, p_, m_) & EQ_OK), b"c9")
+spec_add(9, sig, pk, m, "non-canonical small-order R hashed as given: dalek verify rejects (compares compressed bytes), verify_strict rejects "
+                        "(small order); the verify_batch condition decompresses R and accepts")
+
+
+# 10 / 11: non-canonical small-order A (order 4, y = p), mixed R = [r]B + T', S = r, [k]A + T' = O
+def nc_A(reduced):
+    def build(m):
+        r = honest_r(m)
+        Rm = O.point_add(O.scalarmult(r, B_enc), T4)   # T' of order 4
+        return Rm + le(r), T4_nc
+    return build
+
+
+sig, pk, m = search_nc(nc_A(True), lambda s_, p_, m_: bool(O.flags(s_, T4, m_) & EQ_OK) and not (O.flags(s_, p_, m_) & EQ_OK), b"c10")
+spec_add(10, sig, pk, m, "non-canonical small-order A; equation holds only when A is reduced before hashing (dalek: reject)")
+sig, pk, m = search_nc(nc_A(False), lambda s_, p_, m_: bool(O.flags(s_, p_, m_) & EQ_OK), b"c11")
+spec_add(11, sig, pk, m, "non-canonical small-order A hashed as given: dalek verify accepts, verify_strict rejects (small order)")
+
 # ------------------------------------------------------------------------------------------------ SHA-512 / Digest KATs
 digest_kats = []
 for m in (b"", b"abc", b"abcdefghbcdefghicdefghijdefghijkefghijklfghijklmghijklmnhijklmnoijklmnopjklmnopqklmnopqrlmnopqrsmnopqrstnopqrstu",

@@ -9,7 +9,7 @@
 static std::vector<ge_niels> g_btable;
 static void build_table(std::vector<ge_niels> &t, const ge_ext &P, int W, int windows) {
   const int entries = 1 << (W - 1), block = 64;
-  t.resize((size_t)windows * entries);
+  t.resize((size_t)windows * comb_window_stride(W));
   std::vector<fe> prod(block);
   for (int w = 0; w < windows; w++)
     for (int b = 0; b < entries / block; b++) comb_build_block(t.data(), P, W, w, b * block, block, prod.data());

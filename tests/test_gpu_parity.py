@@ -40,7 +40,7 @@ def test_golden_vectors_variable_length(engine, golden):
         assert bool(a) == v["batch_eq"], v["name"]
 
 
-def test_golden_vectors_committee(engine, golden):
+def test_golden_vectors_committee(engine, oracle, golden):
     vs, sig, pk, msgs = _golden_arrays(golden, only32=True)
     keys, inv = np.unique(pk, axis=0, return_inverse=True)
     valid = engine.committee_register(keys)
@@ -49,8 +49,8 @@ def test_golden_vectors_committee(engine, golden):
         got = engine.verify_committee(inv.astype(np.uint32), sig, digests, msg_idx=np.arange(len(vs), dtype=np.uint32), mode=mode)
         for v, a in zip(vs, got):
             assert bool(a) == v[field], (v["name"], field)
-    for k, ok in zip(keys, valid):
-        assert bool(ok) == any(bool(v["flags"] & 1) or False for v in vs if bytes.fromhex(v["pk"]) == k.tobytes()) or True
+    for k, ok in zip(keys, valid):   # out_valid_bitmap = "the key decompresses" (PublicKey::from_bytes succeeds)
+        assert bool(ok) == oracle.decompress_ok(k.tobytes()), k.tobytes().hex()
     # unknown authority index -> reject
     got = engine.verify_committee(np.array([len(keys) + 5], dtype=np.uint32), sig[:1], digests[:1])
     assert not got[0]
@@ -246,10 +246,12 @@ def test_verify_msgs_chunked_pipeline(engine, oracle):
     assert (got == want).all()
 
 
-@pytest.mark.parametrize("base_window,key_window", [(8, 8), (12, 10), (16, 12), (20, 14), (24, 16)])
+@pytest.mark.parametrize("base_window,key_window", [(8, 8), (12, 10), (16, 12), (20, 14), (24, 16), (24, 15), (24, 13), (24, 14), (24, 9), (24, 11), (22, 12)])
 def test_window_width_independence(oracle, golden, base_window, key_window):
-    """Verdicts must not depend on the comb window widths (table sizes): golden vectors + a random set, generic and
-    committee paths, for the small / medium / default table geometries."""
+    """Verdicts must not depend on the comb window widths (table sizes): golden vectors + a random set + the randomised
+    adversarial set, through the generic, lookup, indexed and hs_verify_qcs paths — for the small / medium table geometries AND
+    the ones the benchmarks run (base 24 with key windows 15 = 4,096 keys, 13 = 10,000 keys, 14, and 9 / 11, where
+    253 mod w hits the recoder's extra-digit cases)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
@@ -269,9 +271,94 @@ def test_window_width_independence(oracle, golden, base_window, key_window):
         assert (e.verify_rec128(r) == want).all()                      # lookup path
         keys, inv = np.unique(pk, axis=0, return_inverse=True)
         e.committee_register(keys)
+        assert e.window_bits == (key_window, base_window)
         got = e.verify_committee(inv.astype(np.uint32), sig, recs[:, 96:], msg_idx=np.arange(len(vs), dtype=np.uint32))
         for v, a in zip(vs, got):
             assert bool(a) == v["strict"], v["name"]
+        got = e.verify_rec128(recs, mode=1)                                 # golden vectors through the lookup path, batch-eq
+        for v, a in zip(vs, got):
+            assert bool(a) == v["batch_eq"], v["name"]
+        # randomised adversarial records: lookup (all keys registered), indexed, and one-call QC verification
+        from oracle_api import make_adversarial
+        adv = make_adversarial(oracle, 4000, seed=500 + 31 * base_window + key_window)
+        ws, we = oracle.verify_rec128(adv, mode=0), oracle.verify_rec128(adv, mode=1)
+        akeys, ainv = np.unique(adv[:, 64:96], axis=0, return_inverse=True)
+        e.committee_register(akeys)
+        assert (e.verify_rec128(adv, mode=0) == ws).all() and (e.verify_rec128(adv, mode=1) == we).all()
+        got = e.verify_committee(ainv.astype(np.uint32), adv[:, :64].copy(), adv[:, 96:].copy(), msg_idx=np.arange(len(adv), dtype=np.uint32), mode=0)
+        assert (got == ws).all()
+        _check_qcs_against_oracle(e, oracle, n_val=23, n_qc=60, seed=key_window)
+    finally:
+        e.close()
+
+
+def _check_qcs_against_oracle(e, oracle, n_val, n_qc, seed):
+    """hs_verify_qcs on a registered committee (indices and key bytes) against the oracle's per-vote batch-eq verdicts."""
+    rng = np.random.default_rng(seed)
+    seeds = rng.integers(0, 256, (n_val, 32), dtype=np.uint8)
+    pks = oracle.keygen_batch(seeds)
+    pre = np.zeros((n_qc, 40), dtype=np.uint8)
+    pre[:, :32] = rng.integers(0, 256, (n_qc, 32), dtype=np.uint8)
+    pre[:, 32:] = np.arange(n_qc, dtype="<u8").view(np.uint8).reshape(n_qc, 8)
+    digests = oracle.digest32_batch(pre.reshape(-1), np.arange(n_qc + 1, dtype=np.uint64) * 40)
+    qi = np.repeat(np.arange(n_qc, dtype=np.uint32), rng.integers(1, n_val, n_qc))
+    n = len(qi)
+    vidx = rng.integers(0, n_val, n).astype(np.uint32)
+    sig = oracle.sign_batch(seeds, pks, vidx, digests[qi].reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+    bad = rng.choice(n, max(1, n // 40), replace=False)
+    sig[bad, rng.integers(0, 64, len(bad))] ^= 0x10
+    want_votes = oracle.verify_rec128(np.concatenate([sig, pks[vidx], digests[qi]], axis=1), mode=1)
+    want_qc = np.ones(n_qc, dtype=bool)
+    np.logical_and.at(want_qc, qi, want_votes)
+    e.committee_register(pks)
+    got_qc, got_votes = e.verify_qcs(pre, sig, qi, validator_idx=vidx, want_votes=True)
+    assert (got_votes == want_votes).all() and (got_qc == want_qc).all()
+    assert (e.verify_qcs(pre, sig, qi, pk=pks[vidx]) == want_qc).all()
+
+
+@pytest.mark.parametrize("n_keys,expect_window", [(4096, 15), (10000, 13)])
+def test_benchmark_sized_committees_with_adversarial_members(engine, oracle, n_keys, expect_window):
+    """The committee sizes of BASELINE configs [1]/[2] (4,096 keys -> 15-bit key windows, 110 GB of tables) and [3] (10,000 keys
+    -> 13-bit): honest keys plus the adversarial generator's keys (mixed order, small order, non-decompressible, non-canonical)
+    registered together; honest + corrupted + adversarial records through the lookup and the indexed path, bit-exact against
+    the oracle."""
+    from hotstuff_b200 import Engine
+    from oracle_api import make_adversarial
+    engine.committee_register(np.zeros((0, 32), np.uint8))      # release the session engine's tables: this test needs the HBM
+    w = make_workload(oracle, 20000, n_keys=n_keys - 600, seed=9000 + n_keys, corrupt_frac=0.03)
+    adv = make_adversarial(oracle, 6000, seed=n_keys)
+    akeys = np.unique(adv[:, 64:96], axis=0)[:600]
+    keys = np.concatenate([w["pks"], akeys], axis=0)
+    keys = keys[np.random.default_rng(1).permutation(len(keys))]
+    assert len(np.unique(keys, axis=0)) == len(keys) <= n_keys
+    recs = np.concatenate([to_rec128(w), adv], axis=0)
+    ws, we = oracle.verify_rec128(recs, mode=0), oracle.verify_rec128(recs, mode=1)
+    e = Engine(0)
+    try:
+        valid = e.committee_register(keys)
+        assert e.window_bits == (expect_window, 24)
+        assert (valid == np.array([oracle.decompress_ok(k.tobytes()) for k in keys])).all()
+        assert (e.verify_rec128(recs, mode=0) == ws).all()           # lookup path; keys outside the 600 take the generic pass
+        assert (e.verify_rec128(recs, mode=1) == we).all()
+        index_of = {k.tobytes(): i for i, k in enumerate(keys)}
+        known = np.array([r[64:96].tobytes() in index_of for r in recs])
+        vidx = np.array([index_of.get(r[64:96].tobytes(), 0) for r in recs], dtype=np.uint32)
+        got = e.verify_committee(vidx[known], recs[known, :64].copy(), recs[known, 96:].copy(), msg_idx=np.arange(int(known.sum()), dtype=np.uint32))
+        assert (got == ws[known]).all() and known.sum() > 20000
+        # incremental epoch change: drop 5 validators, add 3 new ones + one that is already there
+        seeds = np.random.default_rng(2).integers(0, 256, (3, 32), dtype=np.uint8)
+        newpk = oracle.keygen_batch(seeds)
+        removed = np.unique(vidx[known][vidx[known] != 7])[:5]
+        idx = e.committee_update(add=np.concatenate([newpk, keys[7:8]]), remove=removed)
+        assert idx[3] == 7 and set(idx[:3]) <= set(removed) | set(range(len(keys), len(keys) + 3))   # freed or spare slots
+        m = np.random.default_rng(3).integers(0, 256, (3, 32), dtype=np.uint8)
+        sg = oracle.sign_batch(seeds, newpk, np.arange(3, dtype=np.uint32), m.reshape(-1), np.arange(4, dtype=np.uint64) * 32)
+        assert e.verify_committee(idx[:3], sg, m, msg_idx=np.arange(3, dtype=np.uint32)).all()          # new validators verify by index
+        assert e.verify_rec128(np.concatenate([sg, newpk, m], axis=1)).all()                            # ... and by key bytes
+        got = e.verify_committee(vidx[known], recs[known, :64].copy(), recs[known, 96:].copy(), msg_idx=np.arange(int(known.sum()), dtype=np.uint32))
+        gone = np.isin(vidx[known], removed)                                                            # dead slot, or now someone else's key
+        assert gone.any() and not got[gone].any() and (got[~gone] == ws[known][~gone]).all()
+        assert (e.verify_rec128(recs, mode=0) == ws).all()            # by key bytes a removed key is simply unregistered: generic path
     finally:
         e.close()
 
@@ -339,8 +426,22 @@ def test_argument_errors_are_reported_not_crashed(engine):
     bm = (ctypes.c_uint32 * 1)()
     rec = (ctypes.c_uint8 * 128)()
     assert lib.hs_verify_rec128(engine.h, rec, 1, 7, bm) != 0            # unknown mode
+    import numpy as np
     ok = ctypes.c_int(5)
-    assert lib.hs_verify_batch_shared_msg(engine.h, None, None, 0, ctypes.byref(ok), None) != 0 and ok.value == 5 or True
+    assert lib.hs_verify_batch_shared_msg(engine.h, None, None, 0, ctypes.byref(ok), None) != 0   # null digest
+    assert ok.value == 5                                                                         # ... and *all_ok is left untouched
+    # offsets that go backwards are an argument error, not a device fault
+    off = np.array([0, 40, 20, 60], dtype=np.uint64)
+    buf = np.zeros(64, np.uint8)
+    out = np.zeros((3, 32), np.uint8)
+    assert lib.hs_digest32_batch(engine.h, buf.ctypes.data, off.ctypes.data, 3, out.ctypes.data) != 0
+    assert b"non-decreasing" in lib.hs_last_error(engine.h)
+    # a committee-indexed call without a committee is refused (r1: null-pointer device read)
+    engine.committee_register(np.zeros((0, 32), np.uint8))
+    vidx = np.zeros(4, np.uint32)
+    sig = np.zeros((4, 64), np.uint8)
+    bm4 = np.zeros(1, np.uint32)
+    assert lib.hs_verify_committee(engine.h, vidx.ctypes.data, sig.ctypes.data, None, buf.ctypes.data, 1, 4, 0, bm4.ctypes.data) != 0
 
 
 def test_randomised_adversarial_differential(engine, oracle):

@@ -45,7 +45,7 @@ def test_scalar_reduce_and_recode(hostemu):
     for s in [0, 1, L_ORDER - 1, L_ORDER, L_ORDER + 1, 2**252, 2**253, 2**256 - 1]:
         assert hostemu.emu_sc_is_canonical(s.to_bytes(32, "little")) == (1 if s < L_ORDER else 0)
     edge = [0, L_ORDER - 1, 2**253 - 1, 2**252, int("7f" * 31, 16), int("80" * 31, 16), int("77" * 32, 16) % 2**253, int("88" * 32, 16) % 2**253]
-    for W, msb in ((4, 1), (4, 0), (8, 0), (10, 0), (11, 0), (12, 0), (14, 0), (16, 0), (20, 0), (23, 0), (24, 0)):
+    for W, msb in [(4, 1), (4, 0)] + [(w, 0) for w in range(8, 27)]:   # every width the engine can be configured with (11 and 23 divide 253)
         for s in edge + [int(rng.integers(0, 2**62)) * int(rng.integers(0, 2**62)) ** 3 % L_ORDER for _ in range(200)]:
             out = (ctypes.c_int * 80)()
             n = hostemu.emu_sc_digits(W, msb, s.to_bytes(32, "little"), out)
@@ -90,7 +90,7 @@ def test_decompress_and_small_order(hostemu, oracle, golden):
 import pytest
 
 
-@pytest.mark.parametrize("wa,wb", [(10, 12), (8, 8), (12, 16)])
+@pytest.mark.parametrize("wa,wb", [(10, 12), (8, 8), (12, 16), (9, 14), (11, 12), (13, 10)])
 def test_golden_vectors_generic_and_committee_paths(hostemu, golden, wa, wb):
     hostemu.emu_set_windows(wa, wb)
     for v in golden["vectors"]:

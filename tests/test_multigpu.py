@@ -44,15 +44,38 @@ def _worker(rank, world, port, n, out_dir):
     d_bm = torch.zeros((hi - lo + 31) // 32, dtype=torch.int32, device=dev)
     pag = PeerAllGather(e, n, rank, world)
     ok = True
-    for rep in range(3):                      # epochs 1..3
+    # Back-to-back epochs with DIFFERENT inputs per epoch and NO barrier / host synchronisation between them: every epoch's
+    # gathered bitmap is snapshotted by a copy enqueued on the same stream right after the verify call (the documented
+    # contract), while the other rank may already be one epoch ahead.  r1's single result buffer mixed epochs here; the
+    # double buffer must not.  Rank 1 is slowed down on odd epochs and rank 0 on even ones to provoke both orders.
+    n_epochs = 24
+    variants = []
+    for v in range(4):
+        r2 = recs.copy()
+        r2[v::7, 5] ^= np.uint8(1 << v)          # a different set of corrupted signatures per variant
+        variants.append((torch.from_numpy(r2[lo:hi]).to(dev), o.verify_rec128(r2, nthreads=4)))
+    snaps = []
+    spin = torch.empty(1 << 22, dtype=torch.float32, device=dev)
+    for ep in range(n_epochs):
+        d_v, _ = variants[ep % 4]
+        if (ep + rank) % 2 == 0:
+            for _ in range(20):
+                spin.normal_()                    # device-side delay on this rank only
         pag.arm()
-        e.verify_rec128_dev(d_recs, d_bm, hi - lo)
-        torch.cuda.synchronize()
-        dist.barrier()
-        got = np.unpackbits(pag.bitmap().cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
-        ok = ok and bool((got == want).all())
-        dist.barrier()
+        e.verify_rec128_dev(d_v, d_bm, hi - lo)
+        snaps.append(pag.bitmap().clone())        # stream-ordered consumer of this epoch's bitmap
+    torch.cuda.synchronize()
+    for ep, snap in enumerate(snaps):
+        got = np.unpackbits(snap.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        ok = ok and bool((got == variants[ep % 4][1]).all())
     ok = ok and not e.lib.hs_peer_timed_out(e.h)
+    dist.barrier()
+    # an empty shard still takes part in the exchange (n == 0 on one rank)
+    pag.arm()
+    e.verify_rec128_dev(d_recs, d_bm, 0 if rank == 1 else hi - lo)
+    torch.cuda.synchronize()
+    ok = ok and not e.lib.hs_peer_timed_out(e.h)
+    dist.barrier()
     # baseline path gives the same answer
     e.verify_rec128_dev(d_recs, d_bm, hi - lo)
     full = all_gather_bitmap(d_bm, n, world)

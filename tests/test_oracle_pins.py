@@ -205,3 +205,26 @@ def test_adversarial_differential_against_openssl(oracle):
         compared += 1
         differs_from_strict += bool(e) != bool(s)
     assert compared > 5000 and differs_from_strict > 100   # the set exercises the strict / batch-eq gap
+
+
+def test_speccheck_classes_match_published_dalek_rows(oracle, golden):
+    """The 12 case classes of "Taming the many EdDSAs" / ed25519-speccheck, re-constructed in tests/golden/gen_golden.py: the
+    oracle's strict verdict must equal the published `Dalek strict` row (Signature::verify = verify_strict,
+    crypto/src/lib.rs:203) and its per-signature equation verdict the published `Dalek` row, except class 9 (non-canonical R:
+    dalek's non-strict verify compares compressed bytes, the verify_batch condition decompresses R).  The same constructed
+    vectors also reproduce the published LibSodium and BoringSSL/OpenSSL rows with the real libraries, which pins the
+    constructions themselves."""
+    vs = sorted((v for v in golden["vectors"] if v["group"] == "speccheck"), key=lambda v: v["speccheck_class"])
+    assert [v["speccheck_class"] for v in vs] == list(range(12))
+    published_strict = [c == 3 for c in range(12)]
+    published_verify = [c in (0, 1, 2, 3, 11) for c in range(12)]
+    for v in vs:
+        c = v["speccheck_class"]
+        sig, pk, m = bytes.fromhex(v["sig"]), bytes.fromhex(v["pk"]), bytes.fromhex(v["msg"])
+        f = oracle.flags(sig, pk, m)
+        assert f == oracle.flags(sig, pk, m, fast=True) == v["flags"]
+        assert bool(f & STRICT) == published_strict[c] == v["published_dalek_strict"], c
+        assert bool(f & EQ_OK) == (published_verify[c] if c != 9 else True), c
+        assert v["published_dalek_verify"] == published_verify[c]
+        assert v["libsodium"] == published_strict[c], c      # published LibSodium row = X X X V X X X X X X X X
+        assert v["openssl"] == published_verify[c], c        # published BoringSSL / OpenSSL row = V V V V X X X X X X X V
