@@ -479,6 +479,14 @@ def main():
         torch.cuda.synchronize()
         kern.append(k0.elapsed_time(k1))
     kern_ms = float(np.median(kern))
+    dig = []
+    for _ in range(3):   # the Digest kernel on its own (same stream, CUDA events)
+        k0.record()
+        eng.digest32_fixed_dev(d_msgs, L, d_digest, n)
+        k1.record()
+        torch.cuda.synchronize()
+        dig.append(k0.elapsed_time(k1))
+    dig_ms = float(np.median(dig))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -565,6 +573,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>", "cached_keys": eng.cached_keys,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s", "traffic": traffic,
+                         "digest_kernel_ms": dig_ms, "digest_algorithmic_GBps": ALGO_BYTES_DIGEST * n / (dig_ms * 1e-3) / 1e9,
                          "kernel_ms": kern_ms, "kernel_ms_covers": "lookup + main + finish kernels of one verify pass over 2^20 resident records",
                          "algorithmic_bytes_per_verify": ALGO_BYTES_VERIFY,
                          "note": "integer-ALU bound path: 128 B of compulsory I/O per ~0.1-0.3 M INT32 instructions; HBM fraction is necessarily << 1 (SURVEY §0.7)"},

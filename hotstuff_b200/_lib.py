@@ -31,6 +31,7 @@ SIGNATURES = {
     "hs_verify_var_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),
     "hs_verify_committee_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),
     "hs_digest32_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_digest32_fixed_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "hs_peer_setup": (c_int, [c_void_p, c_int, c_int, c_size_t, c_void_p]),
     "hs_peer_open": (c_int, [c_void_p, c_int, c_void_p]),
     "hs_peer_next": (c_int, [c_void_p, c_size_t, c_u32]),

@@ -255,6 +255,143 @@ __global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : 3)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ latency path (n <= 64)
+// One Block::verify / Vote::verify / 3-vote QC of a 4-node deployment is 1 .. 64 signatures (BASELINE config[4]): the
+// throughput kernels above would spend 5 launches and ~28 serial mixed additions + an inversion on it (r1: 155 us per
+// verify).  Here ONE launch of 64-thread blocks does a signature per block: warp 0 hashes, recodes, lets lane j fetch the table
+// entry of digit j and sums the lanes' points with a shuffle tree (5 levels); warp 1 decompresses R meanwhile; thread 0
+// compares projectively.  Inputs and verdicts live in mapped pinned host memory (no copy calls); the last block raises a
+// completion word the host polls.  Registered / cached keys only (the host resolves key bytes to indices first).
+struct small_rec {
+  uint8_t sig[64];
+  uint8_t msg[32];
+  uint32_t vidx;
+  uint32_t pad[7];
+};
+static_assert(sizeof(small_rec) == 128, "small_rec is 128 bytes");
+#define HS_SMALL_MAX 64
+__device__ __forceinline__ void fe_shfl_down(fe &r, const fe &a, int delta) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], delta);
+}
+__global__ void __launch_bounds__(64) k_verify_small(const small_rec *__restrict__ in, uint32_t n, const ge_niels *__restrict__ btable,
+                                                      committee_tables C, const comb_params cp, uint8_t *out_flags, uint32_t *counter,
+                                                      volatile uint32_t *done, uint32_t seq) {
+  __shared__ int32_t dig[HS_MAX_DIGITS];
+  __shared__ fe sh_acc[3], sh_r[2];
+  __shared__ uint32_t sh_meta[2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const small_rec *rec = in + blockIdx.x;
+  uint32_t R[8], S[8];
+  load32(R, rec->sig);
+  load32(S, rec->sig + 32);
+  uint32_t v = rec->vidx;
+  const bool have_key = v < C.n_keys;
+  if (!have_key) v = 0;
+  const uint32_t a_flags = have_key ? C.key_flags[v] : 0u;
+  if (warp == 0) {
+    uint32_t A[8], M[8], h[16], k[8];
+    load32(A, C.pks + (size_t)v * 32);
+    load32(M, rec->msg);
+    sha512_ram32(h, R, A, M);
+    sc_reduce512(k, h);
+    // every lane computes the same digits and stores the same values
+    sc_digits_rt(dig, 1, k, cp.bias_a, cp.wa, cp.na);
+    sc_digits_rt(dig + cp.na, 1, S, cp.bias_b, cp.wb, cp.nb);
+    __syncwarp();
+    const int NT = cp.na + cp.nb;
+    ge_ext acc;
+    ge_identity(acc);
+#pragma unroll 1
+    for (int j = lane; j < NT; j += 32) {  // NT <= 32 for every production geometry: one entry per lane
+      uint32_t neg;
+      bool is_a;
+      const ge_niels *e = comb_entry(C.atables + (size_t)v * C.table_entries, btable, dig, 1, j, cp, neg, is_a);
+      niels_signed q;
+      niels_load_signed(q, e, neg, false);
+      ge_ext p;
+      ge_from_signed_niels(p, q.m0, q.m1);
+      if (j == lane) acc = p;
+      else ge_add_ext(acc, acc, p);
+    }
+#pragma unroll 1
+    for (int step = 1; step < 32; step <<= 1) {
+      ge_ext o;
+      fe_shfl_down(o.X, acc.X, step);
+      fe_shfl_down(o.Y, acc.Y, step);
+      fe_shfl_down(o.Z, acc.Z, step);
+      fe_shfl_down(o.T, acc.T, step);
+      ge_add_ext(acc, acc, o);
+    }
+    if (lane == 0) {
+      sh_acc[0] = acc.X;
+      sh_acc[1] = acc.Y;
+      sh_acc[2] = acc.Z;
+    }
+  } else {
+    ge_ext Rpt;
+    const uint32_t r_ok = ge_decompress(Rpt, R);
+    const uint32_t parse_ok = sc_is_canonical(S) & a_flags & 1u & (have_key ? 1u : 0u);
+    const uint32_t small = ge_enc_is_small_order(R) | ((a_flags >> 1) & 1u);
+    if (lane == 0) {
+      sh_r[0] = Rpt.X;
+      sh_r[1] = Rpt.Y;
+      sh_meta[0] = parse_ok & r_ok;
+      sh_meta[1] = (parse_ok ? HS_F_PARSE_OK : 0u) | (small ? HS_F_SMALL : 0u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t fl = sh_meta[1];
+    const uint32_t eq = sh_meta[0] & ge_proj_equals_affine(sh_acc[0], sh_acc[1], sh_acc[2], sh_r[0], sh_r[1]);
+    if (eq) fl |= HS_F_EQ;
+    if (eq && !(fl & HS_F_SMALL)) fl |= HS_F_STRICT;
+    out_flags[blockIdx.x] = (uint8_t)fl;
+    __threadfence_system();
+    if (atomicAdd(counter, 1u) == n - 1) {
+      *counter = 0;
+      __threadfence_system();
+      *done = seq;
+    }
+  }
+}
+
+// A few LONG messages (one mempool batch is ~15 kB = 120 blocks, mempool/src/processor.rs:30): SHA-512 is sequential in its
+// 80 x nblk rounds, but the message schedule (45 % of the work) of different blocks is independent — lane l of the warp
+// expands block g + l into a shared K+W table, then the rounds run back to back from that table.  One warp per message.
+__global__ void __launch_bounds__(32) k_digest32_long(const uint8_t *__restrict__ data, const uint64_t *__restrict__ off, size_t n,
+                                                       uint32_t *__restrict__ out) {
+  __shared__ uint64_t kw[80 * 32];
+  const size_t i = blockIdx.x;
+  if (i >= n) return;
+  const int lane = threadIdx.x;
+  const uint8_t *m = data + off[i];
+  const uint64_t len = off[i + 1] - off[i];
+  const uint64_t nblk = sha512_nblocks(len);
+  sha512_state s;
+  sha512_init(s);
+#pragma unroll 1
+  for (uint64_t g0 = 0; g0 < nblk; g0 += 32) {
+    if (g0 + lane < nblk) {
+      uint64_t w[16];
+      sha512_block_words(w, m, len, g0 + lane);
+      sha512_expand_kw(kw + lane, 32, w);
+    }
+    __syncwarp();
+    const int cnt = (int)((nblk - g0 < 32) ? (nblk - g0) : 32);
+#pragma unroll 1
+    for (int j = 0; j < cnt; j++) sha512_compress_kw_strided(s, kw + j, 32);  // every lane runs the same rounds (broadcast reads)
+    __syncwarp();
+  }
+  if (lane == 0) {
+    uint32_t h[16];
+    sha512_output_words(s, h);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + i * 8);
+    dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ multi-GPU epilogue
 // The accept bitmap of a sharded verify has to reach every rank (each validator process needs every verdict).  Instead of a
 // separate all-gather collective after the kernel, the finish kernel stores each bitmap word it produces straight into EVERY
@@ -390,8 +527,8 @@ __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_
     if (P.n == 0) {
       bitmap[t >> 1] = word;
     } else {
-#pragma unroll 1
       const size_t at = (P.epoch & 1u) * P.total_words + P.word_offset + (t >> 1);
+#pragma unroll 1
       for (int p = 0; p < P.n; p++) P.buf[p][at] = word;  // fused all-gather: one NVLink store per peer
     }
   }
@@ -557,6 +694,13 @@ struct hs_ctx {
   void *peer_mapped[HS_MAX_PEERS] = {};
   bool peer_armed = false;
   uint32_t peer_epoch = 0;
+  // latency path: mapped pinned staging (inputs, verdict flags, completion word) + device block counter
+  small_rec *h_small_in = nullptr;
+  uint8_t *h_small_out = nullptr;
+  uint32_t *h_small_done = nullptr;
+  uint32_t *d_small_counter = nullptr;
+  uint32_t small_seq = 0;
+  bool small_enabled = true;
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::mutex err_mu;                  // guards err only: fail() is also reached from argument checks taken before `mu`
@@ -823,6 +967,62 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   return HS_OK;
 }
 
+// ---- latency path (host side)
+// key bytes -> table index through the host mirror of the device hash table (registered committee or learned cache)
+static uint32_t host_key_lookup(const hs_ctx *c, const uint8_t *key) {
+  if (c->n_keys == 0 || c->h_slots.empty()) return HS_NO_KEY;
+  uint32_t w[8];
+  memcpy(w, key, 32);
+  uint32_t h = key_hash(w) & c->slot_mask;
+  for (uint32_t probe = 0; probe <= c->slot_mask; probe++) {
+    const uint32_t idx = c->h_slots[h];
+    if (idx == HS_NO_KEY) return HS_NO_KEY;
+    if (idx < c->n_keys && memcmp(c->h_pks.data() + 32 * (size_t)idx, key, 32) == 0) return idx;
+    h = (h + 1) & c->slot_mask;
+  }
+  return HS_NO_KEY;
+}
+static bool small_eligible(const hs_ctx *c, size_t n) { return c->small_enabled && n >= 1 && n <= HS_SMALL_MAX && c->n_keys > 0 && c->d_atables; }
+// c->h_small_in[0 .. n) is filled: one launch, then poll the completion word the last block writes to mapped host memory.
+static int run_small(hs_ctx *c, size_t n, uint32_t mode, uint32_t *out_bitmap, uint8_t *out_flags_or_null) {
+  small_rec *d_in = nullptr;
+  uint8_t *d_out = nullptr;
+  uint32_t *d_done = nullptr;
+  HS_CUDA(c, cudaHostGetDevicePointer(&d_in, c->h_small_in, 0));
+  HS_CUDA(c, cudaHostGetDevicePointer(&d_out, c->h_small_out, 0));
+  HS_CUDA(c, cudaHostGetDevicePointer(&d_done, c->h_small_done, 0));
+  const uint32_t seq = ++c->small_seq ? c->small_seq : ++c->small_seq;  // never 0
+  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
+  k_verify_small<<<(unsigned)n, 64, 0, c->stream>>>(d_in, (uint32_t)n, c->d_btable, C, c->cp, d_out, c->d_small_counter, d_done, seq);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  volatile uint32_t *done = c->h_small_done;
+  bool finished = false;
+  for (uint64_t spin = 0; spin < (1ull << 34); spin++) {
+    if (*done == seq) {
+      finished = true;
+      break;
+    }
+    if ((spin & 0xfff) == 0xfff) {
+      cudaError_t q = cudaStreamQuery(c->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return fail(c, HS_ERR_CUDA, "k_verify_small", q);
+      if (q == cudaSuccess && *done != seq && spin > (1u << 20)) break;  // stream drained without the completion word
+    }
+  }
+  if (!finished) {
+    HS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (*done != seq) return fail(c, HS_ERR_CUDA, "k_verify_small did not complete");
+  }
+  for (size_t w = 0; w < (n + 31) / 32; w++) out_bitmap[w] = 0;
+  const uint32_t want = (mode == HS_MODE_STRICT) ? HS_F_STRICT : HS_F_EQ;
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t fl = ((volatile uint8_t *)c->h_small_out)[i];
+    if (out_flags_or_null) out_flags_or_null[i] = fl;
+    if (fl & want) out_bitmap[i >> 5] |= 1u << (i & 31);
+  }
+  return HS_OK;
+}
+
 // Digest of n fixed-size messages: staged/coalesced kernel when every message starts 16-byte aligned and has at least one
 // full block, the generic per-thread reader otherwise.
 static int launch_digest_fixed(hs_ctx *c, const uint8_t *d_msgs, size_t msg_len, size_t n, uint32_t *d_out, cudaStream_t stream) {
@@ -871,6 +1071,13 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
   if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_in, HS_SMALL_MAX * sizeof(small_rec), cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_out, 256, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_done, 64, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_small_counter, 4);
+  if (e == cudaSuccess) e = cudaMemset(c->d_small_counter, 0, 4);
+  if (e == cudaSuccess) *c->h_small_done = 0;
+  c->small_enabled = !(getenv("HS_SMALL_PATH") && getenv("HS_SMALL_PATH")[0] == '0');
   set_window(c->cp, false, wb);
   set_window(c->cp, true, 12);
   c->wa_forced = (int)((flags >> 8) & 0xffu);
@@ -901,6 +1108,10 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_slots);
   cudaFree(c->d_miss_count);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
+  if (c->h_small_in) cudaFreeHost(c->h_small_in);
+  if (c->h_small_out) cudaFreeHost(c->h_small_out);
+  if (c->h_small_done) cudaFreeHost(c->h_small_done);
+  cudaFree(c->d_small_counter);
   for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->xyz, &c->meta, &c->vidx, &c->miss, &c->out}) cudaFree(b->p);
   cudaFree(c->d_learn_keys);
   cudaFree(c->d_learn_n);
@@ -1137,6 +1348,12 @@ int hs_digest32_dev(hs_ctx *c, const void *d_data, const void *d_off, size_t n, 
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;
 }
+int hs_digest32_fixed_dev(hs_ctx *c, const void *d_msgs, size_t msg_len, size_t n, void *d_out, void *stream) {
+  if (!c || (n && (!d_msgs || !d_out || msg_len == 0))) return fail(c, HS_ERR_ARG, "hs_digest32_fixed_dev: bad argument");
+  if (n == 0) return HS_OK;
+  HS_CUDA(c, cudaSetDevice(c->device));
+  return launch_digest_fixed(c, (const uint8_t *)d_msgs, msg_len, n, (uint32_t *)d_out, (cudaStream_t)stream);
+}
 int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const void *d_vidx, const void *d_msgs, size_t msg_len, size_t n,
                        uint32_t mode, void *d_digests, void *d_bitmap, void *stream) {
   if (!c || mode > 1 || (n && (!d_sig || (!d_pk && !d_vidx) || !d_msgs || !d_digests || !d_bitmap)))
@@ -1269,6 +1486,19 @@ int hs_verify_rec128(hs_ctx *c, const hs_rec128 *recs, size_t n, uint32_t mode, 
   if (n == 0) return HS_OK;
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
+  if (small_eligible(c, n)) {  // latency path: every key must already have a table (registered or learned)
+    bool all = true;
+    for (size_t i = 0; i < n && all; i++) {
+      const uint32_t idx = host_key_lookup(c, recs[i].pk);
+      if (idx == HS_NO_KEY) all = false;
+      else {
+        memcpy(c->h_small_in[i].sig, recs[i].sig, 64);
+        memcpy(c->h_small_in[i].msg, recs[i].msg, 32);
+        c->h_small_in[i].vidx = idx;
+      }
+    }
+    if (all) return run_small(c, n, mode, out_bitmap, nullptr);
+  }
   HS_TRY(ensure(c, c->in[0], n * sizeof(hs_rec128)));
   HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
   HS_CUDA(c, cudaMemcpyAsync(c->in[0].p, recs, n * sizeof(hs_rec128), cudaMemcpyHostToDevice, c->stream));
@@ -1311,6 +1541,30 @@ int hs_verify_batch_shared_msg(hs_ctx *c, const uint8_t digest[32], const hs_vot
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
   size_t words = (n + 31) / 32;
+  if (small_eligible(c, n)) {  // latency path (the 2f+1 = 3 votes of a 4-node QC)
+    bool all = true;
+    for (size_t i = 0; i < n && all; i++) {
+      const uint32_t idx = host_key_lookup(c, votes[i].pk);
+      if (idx == HS_NO_KEY) all = false;
+      else {
+        memcpy(c->h_small_in[i].sig, votes[i].sig, 64);
+        memcpy(c->h_small_in[i].msg, digest, 32);
+        c->h_small_in[i].vidx = idx;
+      }
+    }
+    if (all) {
+      uint32_t bm2[(HS_SMALL_MAX + 31) / 32];
+      HS_TRY(run_small(c, n, HS_MODE_BATCH_EQ, bm2, nullptr));
+      int ok2 = 1;
+      for (size_t w = 0; w < words; w++) {
+        const uint32_t want = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+        if (bm2[w] != want) ok2 = 0;
+        if (out_bitmap_or_null) out_bitmap_or_null[w] = bm2[w];
+      }
+      *all_ok = ok2;
+      return HS_OK;
+    }
+  }
   HS_TRY(ensure(c, c->in[0], n * sizeof(hs_vote) + 32));
   HS_TRY(ensure(c, c->out, words * 4));
   uint8_t *d = (uint8_t *)c->in[0].p;
@@ -1344,6 +1598,14 @@ int hs_verify_committee(hs_ctx *c, const uint32_t *vidx, const uint8_t *sig, con
       if (midx[i] >= n_msgs) return fail(c, HS_ERR_ARG, "hs_verify_committee: msg_idx out of range");
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
+  if (small_eligible(c, n) && c->explicit_committee) {  // latency path
+    for (size_t i = 0; i < n; i++) {
+      memcpy(c->h_small_in[i].sig, sig + 64 * i, 64);
+      memcpy(c->h_small_in[i].msg, digests + 32 * (size_t)(midx ? midx[i] : 0), 32);
+      c->h_small_in[i].vidx = vidx[i];
+    }
+    return run_small(c, n, mode, out_bitmap, nullptr);
+  }
   size_t o_sig = 0, o_v = n * 64, o_m = o_v + n * 4, o_d = o_m + (midx ? n * 4 : 0), total = o_d + n_msgs * 32;
   HS_TRY(ensure(c, c->in[0], total));
   HS_TRY(ensure(c, c->out, ((n + 31) / 32) * 4));
@@ -1369,7 +1631,14 @@ int hs_digest32_batch(hs_ctx *c, const uint8_t *data, const uint64_t *off, size_
   uint8_t *d = (uint8_t *)c->in[0].p;
   HS_CUDA(c, cudaMemcpyAsync(d + o_off, off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   if (off[n]) HS_CUDA(c, cudaMemcpyAsync(d + o_data, data, off[n], cudaMemcpyHostToDevice, c->stream));
-  HS_TRY(hs_digest32_dev(c, d + o_data, d + o_off, n, c->out.p, c->stream));
+  if (n <= 64 && off[n] / n >= 1024) {
+    // a few long messages (mempool batches): one warp per message, schedules expanded in parallel across lanes
+    k_digest32_long<<<(unsigned)n, 32, 0, c->stream>>>(d + o_data, (const uint64_t *)(d + o_off), n, (uint32_t *)c->out.p);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+  } else {
+    HS_TRY(hs_digest32_dev(c, d + o_data, d + o_off, n, c->out.p, c->stream));
+  }
   HS_CUDA(c, cudaMemcpyAsync(out, c->out.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
   HS_CUDA(c, cudaStreamSynchronize(c->stream));
   return HS_OK;

@@ -184,6 +184,45 @@ HS_HD void sha512_compress_kw(sha512_state &s, const sha512_kw &t) {
   }
   s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
 }
+// Same, the K[t] + W[t] words read with a stride (shared-memory table [80][stride] shared by a warp, k_digest32_long).
+HS_HD void sha512_compress_kw_strided(sha512_state &s, const uint64_t *kw, int stride) {
+  uint64_t a = s.h[0], b = s.h[1], c = s.h[2], d = s.h[3], e = s.h[4], f = s.h[5], g = s.h[6], h = s.h[7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int base = 0; base < 80; base += 8) {
+    const uint64_t *q = kw + (size_t)base * stride;
+    HS_SHA_ROUND(a, b, c, d, e, f, g, h, q[0 * stride])
+    HS_SHA_ROUND(h, a, b, c, d, e, f, g, q[1 * stride])
+    HS_SHA_ROUND(g, h, a, b, c, d, e, f, q[2 * stride])
+    HS_SHA_ROUND(f, g, h, a, b, c, d, e, q[3 * stride])
+    HS_SHA_ROUND(e, f, g, h, a, b, c, d, q[4 * stride])
+    HS_SHA_ROUND(d, e, f, g, h, a, b, c, q[5 * stride])
+    HS_SHA_ROUND(c, d, e, f, g, h, a, b, q[6 * stride])
+    HS_SHA_ROUND(b, c, d, e, f, g, h, a, q[7 * stride])
+  }
+  s.h[0] += a; s.h[1] += b; s.h[2] += c; s.h[3] += d; s.h[4] += e; s.h[5] += f; s.h[6] += g; s.h[7] += h;
+}
+// Expands one block's message schedule and parks K[t] + W[t] at kw[t * stride] (t = 0 .. 79); w[16] is consumed.
+HS_HD void sha512_expand_kw(uint64_t *kw, int stride, uint64_t (&w)[16]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 16; j++) kw[(size_t)j * stride] = sha_k(j) + w[j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int base = 16; base < 80; base += 16) {
+    HS_SHA_SCHED(w, 0) HS_SHA_SCHED(w, 1) HS_SHA_SCHED(w, 2) HS_SHA_SCHED(w, 3)
+    HS_SHA_SCHED(w, 4) HS_SHA_SCHED(w, 5) HS_SHA_SCHED(w, 6) HS_SHA_SCHED(w, 7)
+    HS_SHA_SCHED(w, 8) HS_SHA_SCHED(w, 9) HS_SHA_SCHED(w, 10) HS_SHA_SCHED(w, 11)
+    HS_SHA_SCHED(w, 12) HS_SHA_SCHED(w, 13) HS_SHA_SCHED(w, 14) HS_SHA_SCHED(w, 15)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; j++) kw[(size_t)(base + j) * stride] = sha_k(base + j) + w[j];
+  }
+}
 // Host side: K[t] + W[t] of the padding-only block that ends a message of `total_len` bytes (total_len % 128 == 0).
 inline void sha512_pad_schedule(sha512_kw &t, uint64_t total_len) {
   uint64_t w[80];
@@ -286,4 +325,18 @@ HS_HD void sha512_prefix_msg(uint32_t (&out)[16], const uint64_t (&prefix_words)
   sha512_init(s);
   sha512_absorb_blocks(s, prefix_words, n_prefix_words, msg, len, 0, sha512_nblocks((uint64_t)n_prefix_words * 8 + len));
   sha512_output_words(s, out);
+}
+// The 16 message words of block b of msg[0..len) || padding (no prefix).
+HS_HD void sha512_block_words(uint64_t (&w)[16], const uint8_t *msg, uint64_t len, uint64_t b) {
+  const uint64_t nblk = (len + 17 + 127) / 128;
+  const bool aligned8 = ((reinterpret_cast<uintptr_t>(msg) & 7u) == 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 16; j++) {
+    uint64_t v = sha512_msg_word(msg, len, b * 128 + 8 * (uint64_t)j, aligned8);
+    if (b == nblk - 1 && j == 14) v = len >> 61;
+    if (b == nblk - 1 && j == 15) v = len << 3;
+    w[j] = v;
+  }
 }

@@ -189,6 +189,37 @@ HS_HD void ge_comb_ab(ge_ext &acc, const ge_niels *atab, const ge_niels *btab, c
   }
 }
 
+// ---- latency path (one WARP per signature): the na + nb table entries are summed as a binary tree across lanes instead of
+// serially in one thread — 5 levels of point additions instead of 28 — and R is decompressed by a second warp meanwhile,
+// so a single Signature::verify is bounded by one square-root chain, not by 28 mixed additions + an inversion.
+// Entry of (signed) digit d as an extended point.  q holds the entry with its first two coordinates ordered by the sign
+// (niels_load_signed): m1 = y'+x', m0 = y'-x' of the signed point, so X2 = m1 - m0 = 2x', Y2 = m1 + m0 = 2y' and
+// (X : Y : Z : T) = (2 X2 : 2 Y2 : 4 : X2 Y2) is that point scaled by 4 — one multiplication, xy2d not needed.
+HS_HD void ge_from_signed_niels(ge_ext &p, const fe &m0, const fe &m1) {
+  fe x2, y2;
+  fe_sub(x2, m1, m0);
+  fe_add(y2, m1, m0);
+  fe_mul(p.T, x2, y2);
+  fe_add(p.X, x2, x2);
+  fe_add(p.Y, y2, y2);
+  fe_set0(p.Z);
+  p.Z.v[0] = 4;
+}
+// r = p + q, both extended (9M; complete)
+HS_HD void ge_add_ext(ge_ext &r, const ge_ext &p, const ge_ext &q) {
+  ge_cached c;
+  ge_to_cached(c, q);
+  ge_add_cached(r, p, c);
+}
+// Projective equality with an affine point: (X : Y : Z) == (x, y)  <=>  X == x Z and Y == y Z   (Z != 0 on the curve)
+HS_HD uint32_t ge_proj_equals_affine(const fe &X, const fe &Y, const fe &Z, const fe &x, const fe &y) {
+  fe t;
+  fe_mul(t, x, Z);
+  uint32_t ex = fe_eq(t, X);
+  fe_mul(t, y, Z);
+  return ex & fe_eq(t, Y);
+}
+
 // acc = [k]P for an arbitrary point P (already negated by the caller when -A is wanted): radix-16 signed fixed window.
 // tab: 9 cached entries of thread-private scratch (tab[j] = j*P, tab[0] = identity).
 HS_HD void ge_scalarmult_window4(ge_ext &acc, const ge_ext &P, const uint32_t (&k)[8], ge_cached *tab) {

@@ -209,5 +209,8 @@ class Engine:
                                                 None if d_vidx is None else d_vidx.data_ptr(), d_msgs.data_ptr(), msg_len, n, mode,
                                                 d_digests.data_ptr(), d_bitmap.data_ptr(), self._stream()), "hs_verify_msgs_dev")
 
+    def digest32_fixed_dev(self, d_msgs, msg_len, d_out, n):
+        self._check(self.lib.hs_digest32_fixed_dev(self.h, d_msgs.data_ptr(), msg_len, n, d_out.data_ptr(), self._stream()), "hs_digest32_fixed_dev")
+
     def digest32_dev(self, d_data, d_off, d_out, n):
         self._check(self.lib.hs_digest32_dev(self.h, d_data.data_ptr(), d_off.data_ptr(), n, d_out.data_ptr(), self._stream()), "hs_digest32_dev")

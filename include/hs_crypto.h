@@ -134,6 +134,9 @@ int hs_verify_var_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk, const vo
 int hs_verify_committee_dev(hs_ctx *ctx, const void *d_validator_idx, const void *d_sig, const void *d_msg_idx,
                             const void *d_digests, size_t n, uint32_t mode, void *d_bitmap, void *stream);
 int hs_digest32_dev(hs_ctx *ctx, const void *d_data, const void *d_off, size_t n, void *d_out, void *stream);
+/* Digest of n fixed-size messages (msg_len bytes each, concatenated): the transaction / payload shape.  16-byte aligned sizes
+ * >= 128 take the staged kernel (coalesced loads; multiples of 128 also skip the padding block's message schedule). */
+int hs_digest32_fixed_dev(hs_ctx *ctx, const void *d_msgs, size_t msg_len, size_t n, void *d_out, void *stream);
 /* d_digests: n x 32 bytes of scratch that receives Digest(msg_i). */
 int hs_verify_msgs_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk_or_null, const void *d_validator_idx_or_null, const void *d_msgs,
                        size_t msg_len, size_t n, uint32_t mode, void *d_digests, void *d_bitmap, void *stream);

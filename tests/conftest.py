@@ -26,6 +26,7 @@ def hostemu():
     lib = ctypes.CDLL(build.build_hostemu())
     lib.emu_verify_generic.restype = ctypes.c_uint
     lib.emu_verify_committee.restype = ctypes.c_uint
+    lib.emu_verify_committee_tree.restype = ctypes.c_uint
     return lib
 
 

@@ -157,9 +157,94 @@ unsigned emu_verify_committee(const uint8_t sig[64], const uint8_t pk[32], const
   uint32_t meta = verify_committee_main(acc, R, S, h, g_btable.data(), at.data(), (a_ok & 1u) | (a_small << 1), dig, 1, g_cp);
   return finish_one(acc, R, meta);
 }
+// latency path: 32 emulated lanes fetch one table entry each (lane j = digit j), convert it, and a 5-level tree adds them;
+// R is decompressed separately and compared projectively — must give the same flags as the serial committee path.
+unsigned emu_verify_committee_tree(const uint8_t sig[64], const uint8_t pk[32], const uint8_t *msg, uint64_t len) {
+  ensure_btable();
+  uint32_t R[8], S[8], A[8], h[16];
+  load_words(R, sig);
+  load_words(S, sig + 32);
+  load_words(A, pk);
+  ge_ext Apt, negA;
+  uint32_t a_ok = ge_decompress(Apt, A);
+  uint32_t a_small = ge_enc_is_small_order(A);
+  ge_neg(negA, Apt);
+  std::vector<ge_niels> at;
+  if (!a_ok) ge_identity(negA);
+  build_table(at, negA, g_cp.wa, g_cp.na);
+  uint8_t hb[64];
+  emu_sha512_ram(sig, pk, msg, len, hb);
+  memcpy(h, hb, 64);
+  uint32_t k[8];
+  sc_reduce512(k, h);
+  int32_t dig[HS_MAX_DIGITS];
+  sc_digits_rt(dig, 1, k, g_cp.bias_a, g_cp.wa, g_cp.na);
+  sc_digits_rt(dig + g_cp.na, 1, S, g_cp.bias_b, g_cp.wb, g_cp.nb);
+  const int NT = g_cp.na + g_cp.nb;
+  int lanes = 1;
+  while (lanes < NT) lanes <<= 1;
+  std::vector<ge_ext> lane(lanes);
+  for (int j = 0; j < lanes; j++) {
+    if (j < NT) {
+      uint32_t neg;
+      bool is_a;
+      const ge_niels *e = comb_entry(at.data(), g_btable.data(), dig, 1, j, g_cp, neg, is_a);
+      niels_signed q;
+      niels_load_signed(q, e, neg, is_a);
+      ge_from_signed_niels(lane[j], q.m0, q.m1);
+    } else {
+      ge_identity(lane[j]);
+    }
+  }
+  for (int step = 1; step < lanes; step <<= 1)
+    for (int j = 0; j + step < lanes; j += 2 * step) ge_add_ext(lane[j], lane[j], lane[j + step]);
+  ge_ext Rpt;
+  uint32_t r_ok = ge_decompress(Rpt, R);
+  uint32_t parse_ok = sc_is_canonical(S) & a_ok & 1u;
+  uint32_t small = ge_enc_is_small_order(R) | a_small;
+  uint32_t eq = parse_ok & r_ok & ge_proj_equals_affine(lane[0].X, lane[0].Y, lane[0].Z, Rpt.X, Rpt.Y);
+  unsigned fl = 0;
+  if (parse_ok) fl |= HS_F_PARSE_OK;
+  if (eq) fl |= HS_F_EQ;
+  if (small) fl |= HS_F_SMALL;
+  if (eq && !small) fl |= HS_F_STRICT;
+  return fl;
+}
 const uint8_t *emu_btable_bytes(uint64_t *nbytes) {
   ensure_btable();
   *nbytes = g_btable.size() * sizeof(ge_niels);
   return reinterpret_cast<const uint8_t *>(g_btable.data());
 }
+}
+// long-message digest path: schedules expanded per block into a strided K+W table, rounds run from the table
+extern "C" void emu_sha512_kw_path(const uint8_t *msg, uint64_t len, uint8_t out[64]) {
+  sha512_state s;
+  sha512_init(s);
+  const uint64_t nblk = sha512_nblocks(len);
+  std::vector<uint64_t> kw(80 * 32);
+  for (uint64_t g0 = 0; g0 < nblk; g0 += 32) {
+    const int cnt = (int)((nblk - g0 < 32) ? (nblk - g0) : 32);
+    for (int l = 0; l < cnt; l++) {
+      uint64_t w[16];
+      sha512_block_words(w, msg, len, g0 + l);
+      sha512_expand_kw(kw.data() + l, 32, w);
+    }
+    for (int l = 0; l < cnt; l++) sha512_compress_kw_strided(s, kw.data() + l, 32);
+  }
+  uint32_t o[16];
+  sha512_output_words(s, o);
+  memcpy(out, o, 64);
+}
+// padding-only last block through the precomputed schedule (len % 128 == 0)
+extern "C" void emu_sha512_padkw_path(const uint8_t *msg, uint64_t len, uint8_t out[64]) {
+  sha512_state s;
+  sha512_init(s);
+  const uint64_t pre[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  sha512_absorb_blocks(s, pre, 0, msg, len, 0, len / 128);
+  sha512_kw t;
+  sha512_pad_schedule(t, len);
+  sha512_compress_kw(s, t);
+  uint32_t o[16];
+  sha512_output_words(s, o);
+  memcpy(out, o, 64);
 }

@@ -564,3 +564,82 @@ def test_key_cache_resets_when_the_key_set_rotates(oracle, monkeypatch):
         assert 50 <= e.cached_keys < cap                                 # reset happened, the new set was learned
     finally:
         e.close()
+
+
+def test_latency_path_small_batches(engine, oracle, golden):
+    """n <= 64 with every key registered takes the one-launch latency path (k_verify_small: one warp sums the table entries with
+    a shuffle tree, a second warp decompresses R, projective compare).  Golden vectors (incl. the speccheck classes), random
+    and adversarial records in calls of 1 .. 64 records through hs_verify_rec128 / hs_verify_committee /
+    hs_verify_batch_shared_msg must give the oracle's verdicts, and the same verdicts as the throughput path (n > 64)."""
+    from oracle_api import make_adversarial
+    vs, sig, pk, msgs = _golden_arrays(golden, only32=True)
+    recs = np.concatenate([sig, pk, np.array([np.frombuffer(m, np.uint8) for m in msgs])], axis=1)
+    adv = make_adversarial(oracle, 1500, seed=4242)
+    w = make_workload(oracle, 500, n_keys=9, seed=4243, corrupt_frac=0.2)
+    allrecs = np.concatenate([recs, adv, to_rec128(w)], axis=0)
+    ws, we = oracle.verify_rec128(allrecs, mode=0), oracle.verify_rec128(allrecs, mode=1)
+    keys, inv = np.unique(allrecs[:, 64:96], axis=0, return_inverse=True)
+    engine.committee_register(keys)
+    l0 = engine.kernel_launches
+    assert (engine.verify_rec128(allrecs[:64], mode=0) == ws[:64]).all()
+    assert engine.kernel_launches - l0 == 1, "n = 64 with registered keys must be ONE kernel launch"
+    assert (engine.verify_rec128(allrecs, mode=0) == ws).all()            # throughput path, same inputs
+    sizes = [1, 2, 3, 5, 31, 32, 33, 64]
+    lo, k = 0, 0
+    while lo < len(allrecs):
+        n = sizes[k % len(sizes)]
+        k += 1
+        chunk = allrecs[lo:lo + n]
+        assert (engine.verify_rec128(chunk, mode=0) == ws[lo:lo + n]).all(), lo
+        assert (engine.verify_rec128(chunk, mode=1) == we[lo:lo + n]).all(), lo
+        got = engine.verify_committee(inv[lo:lo + n].astype(np.uint32), chunk[:, :64].copy(), chunk[:, 96:].copy(), msg_idx=np.arange(len(chunk), dtype=np.uint32), mode=0)
+        assert (got == ws[lo:lo + n]).all(), lo
+        lo += n
+    # unknown authority index on the latency path -> reject
+    assert not engine.verify_committee(np.array([len(keys) + 9], dtype=np.uint32), allrecs[:1, :64].copy(), allrecs[:1, 96:].copy())[0]
+    # QC of a 4-node committee (3 votes over one digest), valid and with one bad vote
+    seeds = np.random.default_rng(5).integers(0, 256, (4, 32), dtype=np.uint8)
+    pks = oracle.keygen_batch(seeds)
+    engine.committee_register(pks)
+    d = oracle.digest32(bytes(32) + (3).to_bytes(8, "little"))
+    sg = oracle.sign_batch(seeds, pks, np.arange(4, dtype=np.uint32), np.tile(np.frombuffer(d, np.uint8), 4), np.arange(5, dtype=np.uint64) * 32)
+    votes = np.concatenate([pks[1:], sg[1:]], axis=1)
+    l0 = engine.kernel_launches
+    assert engine.verify_batch_shared_msg(d, votes) is True and engine.kernel_launches - l0 == 1
+    votes[1, 40] ^= 1
+    ok, bits = engine.verify_batch_shared_msg(d, votes, want_bitmap=True)
+    assert ok is False and list(bits) == [True, False, True]
+    # a key that is not registered falls back to the throughput path, same verdict
+    other = make_workload(oracle, 3, n_keys=3, seed=77)
+    assert engine.verify_rec128(to_rec128(other)).all()
+    engine.committee_register(np.zeros((0, 32), np.uint8))
+
+
+def test_long_message_digest_kernel(engine):
+    """hs_digest32_batch with a few long messages (mempool batches, ~15 kB) runs the warp-cooperative kernel."""
+    rng = np.random.default_rng(15)
+    lens = [15300, 15301, 1024, 4096, 128 * 33, 128 * 64 + 5, 100000, 2000]
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    data = rng.integers(0, 256, int(off[-1]), dtype=np.uint8)
+    got = engine.digest32_batch(data, off)
+    for i, ln in enumerate(lens):
+        assert got[i].tobytes() == hashlib.sha512(data[int(off[i]):int(off[i + 1])].tobytes()).digest()[:32], ln
+    one = engine.digest32_batch(data[:15300], np.array([0, 15300], dtype=np.uint64))
+    assert one[0].tobytes() == hashlib.sha512(data[:15300].tobytes()).digest()[:32]
+
+
+def test_fixed_length_digest_kernel_shapes(engine, oracle):
+    """hs_verify_msgs with 16-byte aligned message sizes takes the staged digest kernel (k_digest32_fixed): multiples of 128
+    (constant padding block) and others (generic tail), ragged record counts."""
+    for L, n in ((512, 1000), (128, 33), (256, 4097), (144, 500), (640, 31), (1040, 200)):
+        rng = np.random.default_rng(L)
+        seeds = rng.integers(0, 256, (7, 32), dtype=np.uint8)
+        pks = oracle.keygen_batch(seeds)
+        kidx = (np.arange(n) % 7).astype(np.uint32)
+        msgs = rng.integers(0, 256, (n, L), dtype=np.uint8)
+        d = oracle.digest32_batch(msgs.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L)
+        sig = oracle.sign_batch(seeds, pks, kidx, d.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+        sig[::11, 20] ^= 2
+        want = oracle.verify_rec128(np.concatenate([sig, pks[kidx], d], axis=1))
+        assert (engine.verify_msgs(sig, msgs.reshape(-1), L, pk=pks[kidx]) == want).all(), (L, n)

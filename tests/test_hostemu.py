@@ -68,6 +68,21 @@ def test_sha512_paths(hostemu):
         assert o.raw == hashlib.sha512(R + A + m).digest(), ln
 
 
+def test_sha512_schedule_table_paths(hostemu):
+    """The two table-driven compressions of the Digest kernels: per-block K+W tables (k_digest32_long) and the
+    host-expanded padding block of messages whose length is a multiple of 128 (k_digest32_fixed)."""
+    rng = np.random.default_rng(33)
+    o = ctypes.create_string_buffer(64)
+    for ln in [0, 1, 111, 112, 127, 128, 129, 4095, 4096, 4097, 15300, 15301, 128 * 33, 128 * 64 + 5]:
+        m = rng.bytes(ln)
+        hostemu.emu_sha512_kw_path(m, ctypes.c_uint64(ln), o)
+        assert o.raw == hashlib.sha512(m).digest(), ln
+    for ln in [128, 256, 512, 1024, 128 * 33]:
+        m = rng.bytes(ln)
+        hostemu.emu_sha512_padkw_path(m, ctypes.c_uint64(ln), o)
+        assert o.raw == hashlib.sha512(m).digest(), ln
+
+
 def test_decompress_and_small_order(hostemu, oracle, golden):
     rng = np.random.default_rng(4)
     encs = [rng.bytes(32) for _ in range(300)] + [bytes.fromhex(t) for t in golden["torsion_encodings"]]
@@ -100,11 +115,13 @@ def test_golden_vectors_generic_and_committee_paths(hostemu, golden, wa, wb):
         assert got == want, (v["name"], got, want)
     # committee path builds a 384 KB table per key on the CPU: sample the interesting ones
     names = ("rfc8032", "reference")
-    sample = [v for v in golden["vectors"] if v["group"] in names or v["name"].startswith(("adv_valid", "adv_flip_R", "adv_S_", "adv_torsion_pair_eq_1", "adv_identity_A", "adv_mixed_order_A", "adv_A_not_on_curve_0", "adv_zero"))]
+    sample = [v for v in golden["vectors"] if v["group"] in names + ("speccheck",) or v["name"].startswith(("adv_valid", "adv_flip_R", "adv_S_", "adv_torsion_pair_eq_1", "adv_identity_A", "adv_mixed_order_A", "adv_A_not_on_curve_0", "adv_zero"))]
     for v in sample:
         sig, pk, msg = bytes.fromhex(v["sig"]), bytes.fromhex(v["pk"]), bytes.fromhex(v["msg"])
         got = hostemu.emu_verify_committee(sig, pk, msg, ctypes.c_uint64(len(msg)))
         assert got == v["flags"] & ~R_OK, (v["name"], got)
+        if len(msg) == 32 and wa <= 10:   # latency path (tree of lanes + projective compare with the decompressed R)
+            assert hostemu.emu_verify_committee_tree(sig, pk, msg, ctypes.c_uint64(32)) == v["flags"] & ~R_OK, v["name"]
 
 
 def test_random_parity_with_oracle(hostemu, oracle):

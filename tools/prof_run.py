@@ -11,9 +11,14 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 mode = sys.argv[2] if len(sys.argv) > 2 else "committee"
 L = 512
 o = Oracle(); e = Engine(0)
-w = make_workload(o, n, n_keys=4096, seed=3, msg_len=L)
+base = min(n, 1 << 16)            # a signed base set, tiled to n (input synthesis is not what is profiled)
+w = make_workload(o, base, n_keys=4096, seed=3, msg_len=L)
 d = o.digest32_batch(w["msgs"], w["off"], nthreads=16)
-sig = o.sign_batch(w["seeds"], w["pks"], w["key_idx"], d.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+sig = o.sign_batch(w["seeds"], w["pks"], w["key_idx"], d.reshape(-1), np.arange(base + 1, dtype=np.uint64) * 32)
+reps = (n + base - 1) // base
+sig = np.tile(sig, (reps, 1))[:n]
+w["key_idx"] = np.tile(w["key_idx"], reps)[:n]
+w["msgs"] = np.tile(w["msgs"].reshape(base, L), (reps, 1))[:n].reshape(-1)
 dev = torch.device("cuda", 0)
 d_sig = torch.from_numpy(sig).to(dev); d_pk = torch.from_numpy(w["pks"][w["key_idx"]]).to(dev)
 d_msgs = torch.from_numpy(w["msgs"]).to(dev); d_vidx = torch.from_numpy(w["key_idx"].astype(np.int32)).to(dev)
