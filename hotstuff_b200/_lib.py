@@ -22,6 +22,12 @@ SIGNATURES = {
     "hs_verify_var": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p]),
     "hs_verify_batch_shared_msg": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_int), c_void_p]),
     "hs_verify_qcs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_verify_tcs": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_verify_groups": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t,
+                                 c_void_p, c_void_p]),
+    "hs_verify_qc_votes_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_qc_and_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "hs_ingest_consensus_frames": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "hs_committee_register": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "hs_committee_update": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "hs_set_table_budget": (c_int, [c_void_p, c_size_t]),

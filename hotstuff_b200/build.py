@@ -30,11 +30,11 @@ def _sources(d, exts):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "hs_crypto.h")]
+    srcs = _sources(CSRC, (".cu", ".cuh", ".cpp")) + [os.path.join(ROOT, "include", "hs_crypto.h")]
     if not force and _newer(LIB, srcs):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "hs_engine.cu")]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "hs_engine.cu"), os.path.join(CSRC, "hs_ingest.cpp")]
     subprocess.check_call(cmd, cwd=ROOT)
     return LIB
 

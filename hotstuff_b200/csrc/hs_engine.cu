@@ -646,6 +646,56 @@ __global__ void __launch_bounds__(256) k_qc_and(const uint32_t *__restrict__ vot
   }
 }
 
+// item i belongs to group grp[i]; its verdict is flag bit STRICT or EQ by mode[i] (nullptr = all strict).  A rejected item
+// clears its group's bit (group bitmap pre-set to ones); the item verdicts are also packed into item_bitmap (nullable).
+__global__ void __launch_bounds__(256) k_group_and(const uint8_t *__restrict__ flags, const uint8_t *__restrict__ mode, const uint32_t *__restrict__ grp,
+                                                   size_t n_items, size_t n_groups, uint32_t *__restrict__ item_bitmap, uint32_t *__restrict__ group_bitmap) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  uint32_t ok = 0;
+  if (i < n_items) {
+    const uint32_t want = (mode && mode[i] == HS_MODE_BATCH_EQ) ? HS_F_EQ : HS_F_STRICT;
+    ok = (flags[i] & want) ? 1u : 0u;
+    if (!ok) {
+      const uint32_t j = grp[i];
+      if (j < n_groups) atomicAnd(group_bitmap + (j >> 5), ~(1u << (j & 31)));
+    }
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, ok);
+  if (item_bitmap && (threadIdx.x & 31) == 0 && i < n_items) item_bitmap[i >> 5] = word;
+}
+// all-ones bitmap over n bits (unused high bits of the last word 0)
+__global__ void k_bitmap_ones(uint32_t *bm, size_t n) {
+  const size_t w = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const size_t words = (n + 31) / 32;
+  if (w < words) bm[w] = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+}
+// TC::verify (consensus/src/messages.rs:307-311) and Timeout::digest (:268-275): the message of vote i is
+// SHA-512(tc_round_le || high_qc_round_le)[..32] — 16 bytes of which 8 differ per vote; built and hashed here from the two
+// integers (one padded block), so the host ships 8 bytes per vote instead of a digest.
+__global__ void __launch_bounds__(HS_THREADS) k_tc_digests(const uint64_t *__restrict__ tc_round, const uint32_t *__restrict__ tc_idx,
+                                                            const uint64_t *__restrict__ high_qc_round, size_t n, size_t n_tc, uint32_t *__restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = tc_idx ? tc_idx[i] : (uint32_t)i;
+  const uint64_t r = t < n_tc ? tc_round[t] : 0, hq = high_qc_round[i];
+  uint64_t w[16];
+  // to_le_bytes() then read as big-endian message words = byte swap
+  w[0] = ((uint64_t)bswap32((uint32_t)r) << 32) | bswap32((uint32_t)(r >> 32));
+  w[1] = ((uint64_t)bswap32((uint32_t)hq) << 32) | bswap32((uint32_t)(hq >> 32));
+  w[2] = 0x8000000000000000ULL;
+#pragma unroll
+  for (int j = 3; j < 15; j++) w[j] = 0;
+  w[15] = 16 * 8;
+  sha512_state s;
+  sha512_init(s);
+  sha512_compress(s, w);
+  uint32_t h[16];
+  sha512_output_words(s, h);
+  uint4 *dst = reinterpret_cast<uint4 *>(out + i * 8);
+  dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
 // ================================================================================================ host side
 struct dev_buf {
   void *p = nullptr;
@@ -903,7 +953,8 @@ static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_look
 
 // Runs lookup (optional) -> main (committee and/or generic) -> finish on `stream` for a device-resident layout.
 // use_lookup: L.pk is valid and a committee is registered -> resolve indices on the device.
-static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed) {
+static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed,
+                      uint8_t *d_flags_out = nullptr) {
   if (n == 0) {
     if (c->peer_armed) {  // an empty shard still owes its peers the epoch flag
       c->peer_armed = false;
@@ -961,7 +1012,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     P = c->peers;
     c->peer_armed = false;
   }
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, nullptr, P);
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, d_flags_out, P);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;
@@ -1040,6 +1091,13 @@ static int launch_digest_fixed(hs_ctx *c, const uint8_t *d_msgs, size_t msg_len,
   return HS_OK;
 }
 
+// off[0] == 0 and off[i] <= off[i+1]: a decreasing offset would make a length wrap to ~2^64 on the device
+static bool offsets_ok(const uint64_t *off, size_t n) {
+  if (off[0] != 0) return false;
+  for (size_t i = 0; i < n; i++)
+    if (off[i] > off[i + 1]) return false;
+  return true;
+}
 static in_layout layout_rec128(const void *d_recs) {
   const uint8_t *r = (const uint8_t *)d_recs;
   return in_layout{r, 128, r + 64, 128, nullptr, r + 96, 128, nullptr, nullptr, 32, 1};
@@ -1407,6 +1465,126 @@ int hs_verify_qcs(hs_ctx *c, const uint8_t *preimages, size_t n_qc, const uint8_
   return HS_OK;
 }
 
+// ---- device-resident QC verification (strong-scaling path of BASELINE config[3]: the votes of many QCs sharded over ranks)
+// Per-vote verdicts of this rank's shard (batch-eq condition).  d_qc_digests: n_qc x 32 (hs_digest32_fixed_dev over the 40-byte
+// preimages); d_qc_idx selects each vote's digest.  Combine with the (all-gathered) vote bitmap through hs_qc_and_dev.
+int hs_verify_qc_votes_dev(hs_ctx *c, const void *d_qc_digests, const void *d_pk, const void *d_vidx, const void *d_sig, const void *d_qc_idx,
+                           size_t n_votes, void *d_vote_bitmap, void *stream) {
+  if (!c || (n_votes && (!d_qc_digests || (!d_pk && !d_vidx) || !d_sig || !d_qc_idx || !d_vote_bitmap)))
+    return fail(c, HS_ERR_ARG, "hs_verify_qc_votes_dev: bad argument");
+  HS_CUDA(c, cudaSetDevice(c->device));
+  in_layout L{(const uint8_t *)d_sig, 64, (const uint8_t *)d_pk, 32, (const uint32_t *)d_vidx, (const uint8_t *)d_qc_digests, 32,
+              (const uint32_t *)d_qc_idx, nullptr, 32, 0};
+  return run_verify(c, L, n_votes, HS_MODE_BATCH_EQ, (uint32_t *)d_vote_bitmap, (cudaStream_t)stream, d_pk == nullptr);
+}
+// d_qc_bitmap bit j = AND of the verdict bits of the votes with qc_idx == j (no votes -> 1), over a vote bitmap of n_votes bits.
+int hs_qc_and_dev(hs_ctx *c, const void *d_vote_bitmap, const void *d_qc_idx, size_t n_votes, size_t n_qc, void *d_qc_bitmap, void *stream) {
+  if (!c || !d_qc_bitmap || (n_votes && (!d_vote_bitmap || !d_qc_idx))) return fail(c, HS_ERR_ARG, "hs_qc_and_dev: bad argument");
+  HS_CUDA(c, cudaSetDevice(c->device));
+  if (n_qc) k_bitmap_ones<<<blocks_for((n_qc + 31) / 32, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t *)d_qc_bitmap, n_qc);
+  if (n_votes)
+    k_qc_and<<<blocks_for(n_votes, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)d_vote_bitmap, (const uint32_t *)d_qc_idx, n_votes, n_qc,
+                                                                        (uint32_t *)d_qc_bitmap);
+  c->launches += (n_qc ? 1 : 0) + (n_votes ? 1 : 0);
+  HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+
+// ---- TC::verify / Timeout::verify for many certificates (consensus/src/messages.rs:250-265,290-315)
+// Vote i = (key_i, sig_i, high_qc_round_i) of certificate tc_idx[i] (NULL: vote i is its own certificate — the Timeout
+// shape, rounds[i] = Timeout.round); message = SHA-512(tc_round || high_qc_round)[..32] built on the GPU; Signature::verify
+// (strict) per vote; out_tc_bitmap bit j = AND over certificate j.  Stake / duplicate checks (messages.rs:292-304) stay on the host.
+int hs_verify_tcs(hs_ctx *c, const uint64_t *tc_rounds, size_t n_tc, const uint8_t *pk, const uint32_t *vidx, const uint8_t *sig,
+                  const uint64_t *high_qc_rounds, const uint32_t *tc_idx, size_t n_votes, uint32_t *out_vote_bitmap, uint32_t *out_tc_bitmap) {
+  if (!c || !out_tc_bitmap || (n_tc && !tc_rounds) || (n_votes && (!sig || !high_qc_rounds || (!pk && !vidx) || n_tc == 0)) || (!tc_idx && n_votes && n_tc != n_votes))
+    return fail(c, HS_ERR_ARG, "hs_verify_tcs: bad argument");
+  const size_t tc_words = (n_tc + 31) / 32, vote_words = (n_votes + 31) / 32;
+  for (size_t w = 0; w < tc_words; w++) out_tc_bitmap[w] = (w == tc_words - 1 && (n_tc & 31)) ? ((1u << (n_tc & 31)) - 1u) : 0xffffffffu;
+  if (n_votes == 0) return HS_OK;
+  if (tc_idx)
+    for (size_t i = 0; i < n_votes; i++)
+      if (tc_idx[i] >= n_tc) return fail(c, HS_ERR_ARG, "hs_verify_tcs: tc_idx out of range");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  const size_t key_bytes = pk ? 32 : 4;
+  const size_t o_r = 0, o_hq = (n_tc * 8 + 15) & ~(size_t)15, o_dig = o_hq + ((n_votes * 8 + 15) & ~(size_t)15), o_sig = o_dig + n_votes * 32,
+               o_key = o_sig + n_votes * 64, o_ti = o_key + ((n_votes * key_bytes + 15) & ~(size_t)15), total = o_ti + n_votes * 4;
+  HS_TRY(ensure(c, c->in[0], total));
+  HS_TRY(ensure(c, c->out, (vote_words + tc_words) * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
+  uint32_t *d_votes = (uint32_t *)c->out.p, *d_tc = d_votes + vote_words;
+  HS_CUDA(c, cudaMemcpyAsync(d + o_r, tc_rounds, n_tc * 8, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_hq, high_qc_rounds, n_votes * 8, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig, n_votes * 64, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_key, pk ? (const void *)pk : (const void *)vidx, n_votes * key_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (tc_idx) HS_CUDA(c, cudaMemcpyAsync(d + o_ti, tc_idx, n_votes * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d_tc, out_tc_bitmap, tc_words * 4, cudaMemcpyHostToDevice, c->stream));
+  k_tc_digests<<<blocks_for(n_votes), HS_THREADS, 0, c->stream>>>((const uint64_t *)(d + o_r), tc_idx ? (const uint32_t *)(d + o_ti) : nullptr,
+                                                                  (const uint64_t *)(d + o_hq), n_votes, n_tc, (uint32_t *)(d + o_dig));
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  in_layout L{d + o_sig, 64, pk ? d + o_key : nullptr, 32, pk ? nullptr : (const uint32_t *)(d + o_key), d + o_dig, 32, nullptr, nullptr, 32, 0};
+  HS_TRY(run_verify(c, L, n_votes, HS_MODE_STRICT, d_votes, c->stream, pk == nullptr));
+  if (tc_idx) {
+    k_qc_and<<<blocks_for(n_votes, 256), 256, 0, c->stream>>>(d_votes, (const uint32_t *)(d + o_ti), n_votes, n_tc, d_tc);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+    HS_CUDA(c, cudaMemcpyAsync(out_tc_bitmap, d_tc, tc_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    HS_CUDA(c, cudaMemcpyAsync(out_tc_bitmap, d_votes, vote_words * 4, cudaMemcpyDeviceToHost, c->stream));  // one vote per certificate
+  }
+  if (out_vote_bitmap) HS_CUDA(c, cudaMemcpyAsync(out_vote_bitmap, d_votes, vote_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
+// ---- mixed groups: Block::verify for many blocks (messages.rs:54-76) = author signature (strict) + QC votes (batch-eq) + TC
+// votes (strict), all in ONE pass.  Item i signs Digest(preimage[msg_idx[i]]) (variable-length preimages, hashed on the GPU),
+// belongs to group group_idx[i] and is judged by mode[i]; out_group_bitmap bit j = AND over group j's items.
+int hs_verify_groups(hs_ctx *c, const uint8_t *preimages, const uint64_t *pre_off, size_t n_msgs, const uint8_t *sig, const uint8_t *pk,
+                     const uint32_t *vidx, const uint32_t *msg_idx, const uint32_t *group_idx, const uint8_t *mode, size_t n_items, size_t n_groups,
+                     uint32_t *out_item_bitmap, uint32_t *out_group_bitmap) {
+  if (!c || !out_group_bitmap || (n_msgs && !pre_off) || (n_items && (!sig || !msg_idx || !group_idx || (!pk && !vidx) || n_msgs == 0 || n_groups == 0)))
+    return fail(c, HS_ERR_ARG, "hs_verify_groups: bad argument");
+  const size_t g_words = (n_groups + 31) / 32, i_words = (n_items + 31) / 32;
+  for (size_t w = 0; w < g_words; w++) out_group_bitmap[w] = (w == g_words - 1 && (n_groups & 31)) ? ((1u << (n_groups & 31)) - 1u) : 0xffffffffu;
+  if (n_items == 0) return HS_OK;
+  if (!offsets_ok(pre_off, n_msgs) || (pre_off[n_msgs] && !preimages)) return fail(c, HS_ERR_ARG, "hs_verify_groups: bad preimage offsets");
+  for (size_t i = 0; i < n_items; i++)
+    if (msg_idx[i] >= n_msgs || group_idx[i] >= n_groups || (mode && mode[i] > 1)) return fail(c, HS_ERR_ARG, "hs_verify_groups: index out of range");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  const size_t key_bytes = pk ? 32 : 4, pre_bytes = pre_off[n_msgs];
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t o_off = 0, o_pre = al((n_msgs + 1) * 8), o_dig = o_pre + al(pre_bytes + 8), o_sig = o_dig + n_msgs * 32, o_key = o_sig + n_items * 64,
+               o_mi = o_key + al(n_items * key_bytes), o_gi = o_mi + al(n_items * 4), o_mo = o_gi + al(n_items * 4), o_fl = o_mo + al(n_items),
+               total = o_fl + al(n_items);
+  HS_TRY(ensure(c, c->in[0], total));
+  HS_TRY(ensure(c, c->out, (i_words + g_words) * 4));
+  uint8_t *d = (uint8_t *)c->in[0].p;
+  uint32_t *d_items = (uint32_t *)c->out.p, *d_groups = d_items + i_words;
+  HS_CUDA(c, cudaMemcpyAsync(d + o_off, pre_off, (n_msgs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  if (pre_bytes) HS_CUDA(c, cudaMemcpyAsync(d + o_pre, preimages, pre_bytes, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_sig, sig, n_items * 64, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_key, pk ? (const void *)pk : (const void *)vidx, n_items * key_bytes, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_mi, msg_idx, n_items * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_gi, group_idx, n_items * 4, cudaMemcpyHostToDevice, c->stream));
+  if (mode) HS_CUDA(c, cudaMemcpyAsync(d + o_mo, mode, n_items, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d_groups, out_group_bitmap, g_words * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_TRY(hs_digest32_dev(c, d + o_pre, d + o_off, n_msgs, d + o_dig, c->stream));
+  in_layout L{d + o_sig, 64, pk ? d + o_key : nullptr, 32, pk ? nullptr : (const uint32_t *)(d + o_key), d + o_dig, 32, (const uint32_t *)(d + o_mi),
+              nullptr, 32, 0};
+  HS_TRY(run_verify(c, L, n_items, HS_MODE_STRICT, d_items, c->stream, pk == nullptr, d + o_fl));
+  k_group_and<<<blocks_for(n_items, 256), 256, 0, c->stream>>>(d + o_fl, mode ? d + o_mo : nullptr, (const uint32_t *)(d + o_gi), n_items, n_groups, d_items,
+                                                               d_groups);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  if (out_item_bitmap) HS_CUDA(c, cudaMemcpyAsync(out_item_bitmap, d_items, i_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out_group_bitmap, d_groups, g_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
 // ---- multi-GPU peer routing (one process per GPU; handles are exchanged by the host, e.g. torch.distributed.all_gather_object)
 int hs_peer_setup(hs_ctx *c, int rank, int world, size_t total_words, uint8_t handle_out[64]) {
   if (!c || world < 1 || world > HS_MAX_PEERS || rank < 0 || rank >= world || !handle_out || total_words % (size_t)world)
@@ -1467,13 +1645,6 @@ int hs_peer_timed_out(hs_ctx *c) {
 }
 
 // ---- host-pointer entry points
-// off[0] == 0 and off[i] <= off[i+1]: a decreasing offset would make a length wrap to ~2^64 on the device
-static bool offsets_ok(const uint64_t *off, size_t n) {
-  if (off[0] != 0) return false;
-  for (size_t i = 0; i < n; i++)
-    if (off[i] > off[i + 1]) return false;
-  return true;
-}
 static int finish_bitmap(hs_ctx *c, size_t n, uint32_t *out_bitmap) {
   size_t words = (n + 31) / 32;
   HS_CUDA(c, cudaMemcpyAsync(out_bitmap, c->out.p, words * 4, cudaMemcpyDeviceToHost, c->stream));

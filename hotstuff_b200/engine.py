@@ -134,6 +134,43 @@ class Engine:
         out = bitmap_to_bools(qbm, n_qc)
         return (out, bitmap_to_bools(vbm, n)) if want_votes else out
 
+    def verify_tcs(self, tc_rounds, sig, high_qc_rounds, tc_idx=None, pk=None, validator_idx=None, want_votes=False):
+        """TC::verify for many TCs (tc_idx given) or Timeout signatures (tc_idx None: one vote per certificate): the 16-byte
+        digests are built on the GPU from (tc_round, high_qc_round).  Returns bool[n_tc] (and bool[n_votes])."""
+        tr = np.ascontiguousarray(tc_rounds, dtype=np.uint64)
+        hq = np.ascontiguousarray(high_qc_rounds, dtype=np.uint64)
+        sig = _u8(sig, 64).reshape(-1, 64)
+        n, n_tc = sig.shape[0], tr.shape[0]
+        assert hq.shape[0] == n and (pk is None) != (validator_idx is None)
+        ti = None if tc_idx is None else np.ascontiguousarray(tc_idx, dtype=np.uint32)
+        pk = None if pk is None else _u8(pk, 32).reshape(-1, 32)
+        vidx = None if validator_idx is None else np.ascontiguousarray(validator_idx, dtype=np.uint32)
+        tbm = np.zeros(max(1, (n_tc + 31) // 32), dtype=np.uint32)
+        vbm = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32) if want_votes else None
+        self._check(self.lib.hs_verify_tcs(self.h, _ptr(tr) if n_tc else None, n_tc, _ptr(pk), _ptr(vidx), _ptr(sig) if n else None, _ptr(hq) if n else None,
+                                           _ptr(ti), n, _ptr(vbm), _ptr(tbm)), "hs_verify_tcs")
+        out = bitmap_to_bools(tbm, n_tc)
+        return (out, bitmap_to_bools(vbm, n)) if want_votes else out
+
+    def verify_groups(self, preimages, pre_off, sig, msg_idx, group_idx, n_groups, mode=None, pk=None, validator_idx=None, want_items=False):
+        """hs_verify_groups: items over GPU-hashed variable-length preimages, per-item verdict mode, per-group AND."""
+        pre = _u8(preimages)
+        off = np.ascontiguousarray(pre_off, dtype=np.uint64)
+        sig = _u8(sig, 64).reshape(-1, 64)
+        n = sig.shape[0]
+        mi = np.ascontiguousarray(msg_idx, dtype=np.uint32)
+        gi = np.ascontiguousarray(group_idx, dtype=np.uint32)
+        mo = None if mode is None else np.ascontiguousarray(mode, dtype=np.uint8)
+        assert (pk is None) != (validator_idx is None) and mi.shape[0] == n == gi.shape[0]
+        pk = None if pk is None else _u8(pk, 32).reshape(-1, 32)
+        vidx = None if validator_idx is None else np.ascontiguousarray(validator_idx, dtype=np.uint32)
+        gbm = np.zeros(max(1, (n_groups + 31) // 32), dtype=np.uint32)
+        ibm = np.zeros(max(1, (n + 31) // 32), dtype=np.uint32) if want_items else None
+        self._check(self.lib.hs_verify_groups(self.h, _ptr(pre) if pre.size else None, _ptr(off), off.shape[0] - 1, _ptr(sig) if n else None, _ptr(pk), _ptr(vidx),
+                                              _ptr(mi) if n else None, _ptr(gi) if n else None, _ptr(mo), n, n_groups, _ptr(ibm), _ptr(gbm)), "hs_verify_groups")
+        out = bitmap_to_bools(gbm, n_groups)
+        return (out, bitmap_to_bools(ibm, n)) if want_items else out
+
     def committee_register(self, pks):
         pks = _u8(pks, 32).reshape(-1, 32)
         n = pks.shape[0]
@@ -208,6 +245,15 @@ class Engine:
         self._check(self.lib.hs_verify_msgs_dev(self.h, d_sig.data_ptr(), None if d_pk is None else d_pk.data_ptr(),
                                                 None if d_vidx is None else d_vidx.data_ptr(), d_msgs.data_ptr(), msg_len, n, mode,
                                                 d_digests.data_ptr(), d_bitmap.data_ptr(), self._stream()), "hs_verify_msgs_dev")
+
+    def verify_qc_votes_dev(self, d_qc_digests, d_sig, d_qc_idx, d_vote_bitmap, n, d_pk=None, d_vidx=None):
+        self._check(self.lib.hs_verify_qc_votes_dev(self.h, d_qc_digests.data_ptr(), None if d_pk is None else d_pk.data_ptr(),
+                                                    None if d_vidx is None else d_vidx.data_ptr(), d_sig.data_ptr(), d_qc_idx.data_ptr(), n,
+                                                    d_vote_bitmap.data_ptr(), self._stream()), "hs_verify_qc_votes_dev")
+
+    def qc_and_dev(self, d_vote_bitmap, d_qc_idx, n_votes, n_qc, d_qc_bitmap):
+        self._check(self.lib.hs_qc_and_dev(self.h, d_vote_bitmap.data_ptr(), d_qc_idx.data_ptr(), n_votes, n_qc, d_qc_bitmap.data_ptr(), self._stream()),
+                    "hs_qc_and_dev")
 
     def digest32_fixed_dev(self, d_msgs, msg_len, d_out, n):
         self._check(self.lib.hs_digest32_fixed_dev(self.h, d_msgs.data_ptr(), msg_len, n, d_out.data_ptr(), self._stream()), "hs_digest32_fixed_dev")

@@ -98,6 +98,62 @@ int hs_verify_qcs(hs_ctx *ctx, const uint8_t *preimages, size_t n_qc, const uint
                   const uint8_t *sig /* n_votes x 64 */, const uint32_t *qc_idx, size_t n_votes, uint32_t *out_vote_bitmap_or_null,
                   uint32_t *out_qc_bitmap);
 
+/* ---- TC::verify / Timeout::verify for many certificates (consensus/src/messages.rs:250-265,290-315) ------------------------ */
+/* Vote i = (key_i, sig_i, high_qc_rounds[i]) of certificate tc_idx[i]; its message is SHA-512(tc_rounds[tc_idx[i]]_le ||
+ * high_qc_rounds[i]_le)[..32], built and hashed ON THE GPU (messages.rs:307-311: n digests that differ in 8 bytes), judged with
+ * Signature::verify (strict).  out_tc_bitmap bit j = AND over certificate j's votes (no votes -> 1).  tc_idx == NULL: vote i is
+ * its own certificate (n_tc == n_votes) — the shape of n Timeout messages (Timeout::digest, messages.rs:268-275; the embedded
+ * high_qc goes through hs_verify_qcs).  The stake / duplicate checks of messages.rs:292-304 stay on the host. */
+int hs_verify_tcs(hs_ctx *ctx, const uint64_t *tc_rounds, size_t n_tc, const uint8_t *pk_or_null, const uint32_t *validator_idx_or_null,
+                  const uint8_t *sig /* n_votes x 64 */, const uint64_t *high_qc_rounds, const uint32_t *tc_idx_or_null, size_t n_votes,
+                  uint32_t *out_vote_bitmap_or_null, uint32_t *out_tc_bitmap);
+
+/* ---- mixed groups: Block::verify for many blocks in one pass (consensus/src/messages.rs:54-76) ------------------------------ */
+/* Item i signs Digest(preimages[pre_off[msg_idx[i]] .. pre_off[msg_idx[i]+1])) (hashed on the GPU), belongs to group group_idx[i]
+ * and is judged by mode[i] (HS_MODE_*; NULL = all strict): a block is one group holding its author signature (strict, Block::digest
+ * preimage :79-90), its QC's votes (batch-eq, 40-byte preimage) and its TC's votes (strict, 16-byte preimages).
+ * out_group_bitmap bit j = AND over group j's items. */
+int hs_verify_groups(hs_ctx *ctx, const uint8_t *preimages, const uint64_t *pre_off /* n_msgs + 1 */, size_t n_msgs, const uint8_t *sig /* n_items x 64 */,
+                     const uint8_t *pk_or_null, const uint32_t *validator_idx_or_null, const uint32_t *msg_idx, const uint32_t *group_idx,
+                     const uint8_t *mode_or_null, size_t n_items, size_t n_groups, uint32_t *out_item_bitmap_or_null, uint32_t *out_group_bitmap);
+
+/* ---- wire-format ingest: bincode ConsensusMessage frames -> the arrays hs_verify_groups consumes ------------------------------ */
+/* Replaces `bincode::deserialize::<ConsensusMessage>` + the per-signature walk of Block/Vote/Timeout/TC::verify
+ * (consensus/src/consensus.rs:33-39,138; crypto/src/lib.rs:94-112 PublicKey = base64 *string*; :178-182 Signature = 2 x 32 raw bytes)
+ * for the crypto path: frame i (frames[off[i] .. off[i+1])) becomes group i; every signature in it becomes one item (signature,
+ * decoded key bytes, preimage index, verdict mode) and every digest preimage is laid out for on-GPU hashing:
+ *   Propose(Block): author item (strict, Block::digest preimage) + QC votes (batch-eq; skipped for the genesis QC) + TC votes (strict)
+ *   Vote: one strict item      Timeout: author item (strict, 16-byte preimage) + high_qc votes      TC: its votes (strict)
+ * Host-only, stateless, thread-safe.  Output buffers are caller-owned (hs_host_alloc() them to make the following H2D copies DMA
+ * directly).  Returns HS_OK, or HS_ERR_NOMEM when a capacity is too small — n_items / n_msgs / pre_bytes then hold the required
+ * sizes.  A malformed frame (truncated, bad tag, bad base64, absurd length) gets kind HS_FRAME_MALFORMED and contributes no items
+ * (the reference drops it with SerializationError).  The stake / duplicate pre-checks of messages.rs stay with the caller: the
+ * item ranges in hs_frame_info say which keys belong to which certificate. */
+#define HS_NO_ITEM 0xffffffffu
+#define HS_FRAME_MALFORMED 255
+typedef struct {
+  uint8_t kind;          /* ConsensusMessage tag: 0 Propose, 1 Vote, 2 Timeout, 3 TC, 4 SyncRequest; HS_FRAME_MALFORMED */
+  uint8_t has_tc;        /* Block.tc is Some / the frame is a TC */
+  uint8_t qc_is_genesis; /* embedded QC == QC::genesis(): not verified upstream (messages.rs:67,261) */
+  uint8_t pad;
+  uint32_t author_item;  /* item of the author's signature (HS_NO_ITEM for TC / SyncRequest) */
+  uint32_t qc_lo, qc_hi; /* items of the embedded QC's votes [lo, hi) */
+  uint32_t tc_lo, tc_hi; /* items of the TC's votes [lo, hi) */
+  uint64_t round, qc_round, tc_round;
+} hs_frame_info;
+typedef struct {
+  size_t cap_items, cap_msgs, cap_pre_bytes; /* in: capacities */
+  uint8_t *sig;        /* cap_items x 64 */
+  uint8_t *pk;         /* cap_items x 32 */
+  uint32_t *msg_idx;   /* cap_items */
+  uint32_t *group_idx; /* cap_items (= frame index) */
+  uint8_t *mode;       /* cap_items: HS_MODE_* */
+  uint8_t *preimages;  /* cap_pre_bytes */
+  uint64_t *pre_off;   /* cap_msgs + 1 */
+  size_t n_items, n_msgs, pre_bytes; /* out */
+} hs_ingest_out;
+int hs_ingest_consensus_frames(const uint8_t *frames, const uint64_t *off /* n + 1 */, size_t n, hs_frame_info *info /* n */, hs_ingest_out *out);
+
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
 /* Decompresses every key and builds its comb table in HBM (window 16 bits: 48 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
@@ -140,6 +196,13 @@ int hs_digest32_fixed_dev(hs_ctx *ctx, const void *d_msgs, size_t msg_len, size_
 /* d_digests: n x 32 bytes of scratch that receives Digest(msg_i). */
 int hs_verify_msgs_dev(hs_ctx *ctx, const void *d_sig, const void *d_pk_or_null, const void *d_validator_idx_or_null, const void *d_msgs,
                        size_t msg_len, size_t n, uint32_t mode, void *d_digests, void *d_bitmap, void *stream);
+
+/* QC votes of this rank's shard (per-vote verify_batch condition) over precomputed QC digests (hs_digest32_fixed_dev over the
+ * 40-byte preimages), and the per-QC AND over a (possibly all-gathered) vote bitmap — the device-resident pieces of
+ * hs_verify_qcs, used when the votes of many QCs are sharded across GPUs (BASELINE config[3]). */
+int hs_verify_qc_votes_dev(hs_ctx *ctx, const void *d_qc_digests, const void *d_pk_or_null, const void *d_validator_idx_or_null, const void *d_sig,
+                           const void *d_qc_idx, size_t n_votes, void *d_vote_bitmap, void *stream);
+int hs_qc_and_dev(hs_ctx *ctx, const void *d_vote_bitmap, const void *d_qc_idx, size_t n_votes, size_t n_qc, void *d_qc_bitmap, void *stream);
 
 /* ---- multi-GPU: fused all-gather of the accept bitmap (one process per GPU, same node, NVLink) ------------------------
  * Each rank creates a result buffer for the GLOBAL bitmap (total_words) and exports a 64-byte CUDA-IPC handle; the host
