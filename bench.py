@@ -37,46 +37,38 @@ ALGO_BYTES_DIGEST = 512 + 32  # bytes hashed + digest out
 
 
 # ------------------------------------------------------------------------------------------------ input synthesis
-def _sign_chunk(args):
-    """Worker: RFC 8032 signatures from OpenSSL (independent of both the engine and the oracle)."""
-    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
-    seeds, key_idx, digests = args
-    keys = {}
-    out = np.zeros((len(key_idx), 64), dtype=np.uint8)
-    for i, k in enumerate(key_idx):
-        sk = keys.get(k)
-        if sk is None:
-            sk = keys[k] = Ed25519PrivateKey.from_private_bytes(seeds[k].tobytes())
-        out[i] = np.frombuffer(sk.sign(digests[i].tobytes()), dtype=np.uint8)
-    return out
-
-
-def make_inputs(n, n_keys, msg_len, seed, corrupt_frac=0.01):
+def make_inputs(n, n_keys, msg_len, seed, corrupt_frac=0.01, engine=None, oracle=None):
     """Synthetic workload of SURVEY §8(d) config 2: n records, n_keys distinct keys (i mod n_keys), msg_len-byte messages
     shaped like the bench client's transactions (node/src/client.rs:112-120: tag byte, u64 counter, padding), signatures
-    over Digest(msg) made with OpenSSL, then corrupt_frac of the records get one flipped bit in sig|pk|msg."""
-    from concurrent.futures import ProcessPoolExecutor
-    from cryptography.hazmat.primitives import serialization
-    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    over Digest(msg), then corrupt_frac of the records get one flipped bit in sig|pk|msg.
+    Signing is RFC 8032 (deterministic), so WHO signs does not change the bytes: the GPU arm uses the engine's load-generation
+    signer (hs_keygen_batch / hs_sign_digests: 2^20 signatures in milliseconds instead of a minute of host time) and cross-checks
+    a sample against OpenSSL; the reference arm (no engine allowed on that path) uses the oracle's signer."""
     import hashlib
     rng = np.random.default_rng(seed)
     seeds = rng.integers(0, 256, size=(n_keys, 32), dtype=np.uint8)
-    pks = np.zeros((n_keys, 32), dtype=np.uint8)
-    for k in range(n_keys):
-        pks[k] = np.frombuffer(Ed25519PrivateKey.from_private_bytes(seeds[k].tobytes()).public_key().public_bytes(
-            serialization.Encoding.Raw, serialization.PublicFormat.Raw), dtype=np.uint8)
     msgs = rng.integers(0, 256, size=(n, msg_len), dtype=np.uint8)
     msgs[:, 0] = 1
     msgs[:, 1:9] = np.arange(n, dtype=">u8").view(np.uint8).reshape(n, 8)
     key_idx = (np.arange(n) % n_keys).astype(np.uint32)
-    digests = np.zeros((n, 32), dtype=np.uint8)
-    for i in range(n):
-        digests[i] = np.frombuffer(hashlib.sha512(msgs[i].tobytes()).digest()[:32], dtype=np.uint8)
-    nproc = max(1, min(64, host_cores()))
-    chunks = np.array_split(np.arange(n), nproc * 4)
-    with ProcessPoolExecutor(max_workers=nproc) as ex:
-        parts = list(ex.map(_sign_chunk, [(seeds, key_idx[c], digests[c]) for c in chunks if len(c)]))
-    sig = np.concatenate(parts, axis=0)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(msg_len)
+    if engine is not None:
+        pks = engine.keygen_batch(seeds)
+        digests = np.concatenate([engine.digest32_batch(msgs[lo:lo + (1 << 18)].reshape(-1), off[:min(1 << 18, n - lo) + 1])
+                                  for lo in range(0, n, 1 << 18)], axis=0)
+        sig = engine.sign_digests(seeds, pks, digests, key_idx=key_idx)
+        # independent cross-check of the synthesis itself (OpenSSL + hashlib) on a sample
+        from cryptography.hazmat.primitives import serialization
+        from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+        for i in rng.choice(n, size=min(n, 256), replace=False):
+            sk = Ed25519PrivateKey.from_private_bytes(seeds[key_idx[i]].tobytes())
+            d = hashlib.sha512(msgs[i].tobytes()).digest()[:32]
+            assert d == digests[i].tobytes() and sk.sign(d) == sig[i].tobytes(), "GPU-synthesised input %d differs from OpenSSL" % i
+            assert sk.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw) == pks[key_idx[i]].tobytes()
+    else:
+        pks = oracle.keygen_batch(seeds)
+        digests = oracle.digest32_batch(msgs.reshape(-1), off, nthreads=host_cores())
+        sig = oracle.sign_batch(seeds, pks, key_idx, digests.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32, nthreads=host_cores())
     pk = pks[key_idx].copy()
     corrupted = np.zeros(n, dtype=bool)
     k = int(n * corrupt_frac)
@@ -178,7 +170,7 @@ def run_reference(args):
     oracle = Oracle()
     cores = host_cores()
     sample = min(args.n, args.ref_sample)
-    inp = make_inputs(sample, min(args.keys, sample), args.msg_len, seed=1234, corrupt_frac=0.01)
+    inp = make_inputs(sample, min(args.keys, sample), args.msg_len, seed=1234, corrupt_frac=0.01, oracle=oracle)
     for _ in range(args.warmup):
         cpu_reference_step(oracle, inp, 0, min(sample, 4096), cores)
     times = []
@@ -209,19 +201,15 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------------------ QC workload (configs 2/3)
-def make_qc_inputs(n_val, n_qc, votes_per_qc, seed):
+def make_qc_inputs(eng, n_val, n_qc, votes_per_qc, seed):
     """Committee of n_val validators; n_qc QCs, each with votes_per_qc distinct signers over QC::digest =
-    SHA-512(hash || round_le)[..32] (consensus/src/messages.rs:201-208).  1 % of the votes get one flipped signature bit."""
-    from concurrent.futures import ProcessPoolExecutor
-    from cryptography.hazmat.primitives import serialization
-    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    SHA-512(hash || round_le)[..32] (consensus/src/messages.rs:201-208).  1 % of the votes get one flipped signature bit.
+    Keys and signatures come from the engine's load-generation signer (RFC 8032, cross-checked against OpenSSL on a sample)."""
     import hashlib
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
     rng = np.random.default_rng(seed)
     seeds = rng.integers(0, 256, size=(n_val, 32), dtype=np.uint8)
-    pks = np.zeros((n_val, 32), dtype=np.uint8)
-    for k in range(n_val):
-        pks[k] = np.frombuffer(Ed25519PrivateKey.from_private_bytes(seeds[k].tobytes()).public_key().public_bytes(
-            serialization.Encoding.Raw, serialization.PublicFormat.Raw), dtype=np.uint8)
+    pks = eng.keygen_batch(seeds)
     pre = np.zeros((n_qc, 40), dtype=np.uint8)
     pre[:, :32] = rng.integers(0, 256, size=(n_qc, 32), dtype=np.uint8)
     pre[:, 32:] = np.arange(1, n_qc + 1, dtype="<u8").view(np.uint8).reshape(n_qc, 8)
@@ -229,11 +217,9 @@ def make_qc_inputs(n_val, n_qc, votes_per_qc, seed):
     n = n_qc * votes_per_qc
     vidx = np.concatenate([rng.choice(n_val, size=votes_per_qc, replace=False) for _ in range(n_qc)]).astype(np.uint32)
     midx = np.repeat(np.arange(n_qc, dtype=np.uint32), votes_per_qc)
-    nproc = max(1, min(64, host_cores()))
-    chunks = np.array_split(np.arange(n), nproc * 4)
-    with ProcessPoolExecutor(max_workers=nproc) as ex:
-        parts = list(ex.map(_sign_chunk, [(seeds, vidx[c], digests[midx[c]]) for c in chunks if len(c)]))
-    sig = np.concatenate(parts, axis=0)
+    sig = eng.sign_digests(seeds, pks, digests[midx], key_idx=vidx)
+    for i in rng.choice(n, size=64, replace=False):
+        assert Ed25519PrivateKey.from_private_bytes(seeds[vidx[i]].tobytes()).sign(digests[midx[i]].tobytes()) == sig[i].tobytes()
     bad = rng.choice(n, size=n // 100, replace=False)
     sig[bad, rng.integers(0, 64, bad.shape[0])] ^= (1 << rng.integers(0, 8, bad.shape[0])).astype(np.uint8)
     corrupted = np.zeros(n, dtype=bool)
@@ -241,36 +227,27 @@ def make_qc_inputs(n_val, n_qc, votes_per_qc, seed):
     return dict(pks=pks, pre=pre, digests=digests, vidx=vidx, midx=midx, sig=sig, corrupted=corrupted)
 
 
-def run_qc(args):
-    import torch
-    import torch.distributed as dist
-    from hotstuff_b200 import Engine, build
+def qc_leg(eng, torch, dist, dev, rank, world, committee, qcs, votes_per_qc, steps, warmup, collective):
+    """One QC-verification measurement: QC::digest for every certificate, the verify_batch condition per vote of THIS rank's
+    shard, all-gather of the vote bitmaps (fused peer stores or ncclAllGather), per-QC AND over the gathered bitmap — every rank
+    ends with every QC verdict.  STRONG scaling: the total number of votes is fixed.  Engine kernels only inside the timed region."""
     from hotstuff_b200.sharding import shard_range, all_gather_bitmap
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    build.build_engine()
-    eng = Engine(local_rank)
-    inp = make_qc_inputs(args.committee, args.qcs, args.votes_per_qc, seed=4321)   # identical on every rank (seeded)
+    inp = make_qc_inputs(eng, committee, qcs, votes_per_qc, seed=4321)   # identical on every rank (seeded)
     n = inp["sig"].shape[0]
     lo, hi, per = shard_range(n, rank, world)
     assert eng.committee_register(inp["pks"]).all()
     d_pre = torch.from_numpy(inp["pre"].reshape(-1)).to(dev)
-    d_off = torch.arange(args.qcs + 1, dtype=torch.int64, device=dev) * 40
-    d_dig = torch.empty((args.qcs, 32), dtype=torch.uint8, device=dev)
+    d_dig = torch.empty((qcs, 32), dtype=torch.uint8, device=dev)
     d_sig = torch.from_numpy(inp["sig"][lo:hi]).to(dev)
     d_vidx = torch.from_numpy(inp["vidx"][lo:hi].astype(np.int32)).to(dev)
     d_midx = torch.from_numpy(inp["midx"][lo:hi].astype(np.int32)).to(dev)
-    d_midx_all = torch.from_numpy(inp["midx"].astype(np.int64)).to(dev)
+    d_midx_all = torch.from_numpy(inp["midx"].astype(np.int32)).to(dev)
     words_local = (hi - lo + 31) // 32
-    d_bm = torch.zeros(max(1, words_local), dtype=torch.int32, device=dev)
-    d_idx = torch.arange(n, dtype=torch.int64, device=dev)
+    d_bm = torch.zeros(max(1, per // 32), dtype=torch.int32, device=dev)
+    d_full = torch.zeros((per // 32) * world, dtype=torch.int32, device=dev)
+    d_qc = torch.zeros((qcs + 31) // 32, dtype=torch.int32, device=dev)
     pag = None
-    if world > 1 and args.collective == "peer":
+    if world > 1 and collective == "peer":
         from hotstuff_b200.sharding import PeerAllGather
         try:
             pag = PeerAllGather(eng, n, rank, world)
@@ -279,33 +256,36 @@ def run_qc(args):
                 print("peer all-gather unavailable, using ncclAllGather: %s" % ex, file=sys.stderr)
 
     def step():
-        eng.digest32_dev(d_pre, d_off, d_dig, args.qcs)                                    # QC::digest for every certificate
+        eng.digest32_fixed_dev(d_pre, 40, d_dig, qcs)                                       # QC::digest for every certificate
         if pag is not None:
             pag.arm()
-        eng.verify_committee_dev(d_vidx, d_sig, d_dig, d_bm, hi - lo, d_midx=d_midx, mode=1)  # verify_batch condition per vote
-        full = pag.bitmap() if pag is not None else all_gather_bitmap(d_bm[:words_local], n, world)  # every rank gets every verdict
-        bits = (full[d_idx >> 5] >> (d_idx & 31)) & 1
-        qc_ok = torch.ones(args.qcs, dtype=torch.int32, device=dev).scatter_reduce(0, d_midx_all, bits.to(torch.int32), reduce="amin")
-        return full, qc_ok
+        eng.verify_qc_votes_dev(d_dig, d_sig, d_midx, d_bm, hi - lo, d_vidx=d_vidx)          # verify_batch condition per vote (this shard)
+        if pag is not None:
+            full = pag.bitmap()
+        elif world > 1:
+            dist.all_gather_into_tensor(d_full, d_bm)
+            full = d_full
+        else:
+            full = d_bm
+        eng.qc_and_dev(full, d_midx_all, n, qcs, d_qc)                                      # per-QC AND over ALL votes, on every rank
+        return full
 
-    for _ in range(max(3, args.warmup)):
-        full, qc_ok = step()
+    for _ in range(max(3, warmup)):
+        full = step()
     torch.cuda.synchronize()
     bits = np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     assert (bits == ~inp["corrupted"]).all(), "vote verdicts differ from the expected pattern"
-    want_qc = np.ones(args.qcs, dtype=bool)
+    want_qc = np.ones(qcs, dtype=bool)
     np.logical_and.at(want_qc, inp["midx"], ~inp["corrupted"])
-    assert (qc_ok.cpu().numpy().astype(bool) == want_qc).all(), "per-QC AND differs"
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    got_qc = np.unpackbits(d_qc.cpu().numpy().view(np.uint8), bitorder="little")[:qcs].astype(bool)
+    assert (got_qc == want_qc).all(), "per-QC AND differs"
     l0 = eng.kernel_launches
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
@@ -315,19 +295,42 @@ def run_qc(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    wa, wb = eng.window_bits
+    return {"votes": n, "committee": committee, "qcs": qcs, "votes_per_qc": votes_per_qc, "ms_per_step": ms / steps, "votes_per_s": n * steps / (ms * 1e-3),
+            "gpu_launches_per_step": int(eng.kernel_launches - l0) // steps, "window_bits": {"key": wa, "base": wb}, "votes_per_rank": per,
+            "collective": "none (1 rank)" if world == 1 else ("fused peer-store all-gather inside the finish kernel (NVLink P2P)" if pag is not None else "ncclAllGather"),
+            "scaling": "strong"}
+
+
+def run_qc(args):
+    import torch
+    import torch.distributed as dist
+    from hotstuff_b200 import Engine, build
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    build.build_engine()
+    eng = Engine(local_rank, base_window=args.base_window)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    r = qc_leg(eng, torch, dist, dev, rank, world, args.committee, args.qcs, args.votes_per_qc, args.steps, args.warmup, args.collective)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        wa, wb = eng.window_bits
         print(json.dumps({
-            "metric": "Ed25519 verifies/s", "value": n * args.steps / (ms * 1e-3), "unit": "verifies/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic", "gpu_launches": int(eng.kernel_launches - l0), "clocks": clocks,
+            "metric": "Ed25519 verifies/s", "value": r["votes_per_s"], "unit": "verifies/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic", "gpu_launches": r["gpu_launches_per_step"] * args.steps, "clocks": clocks,
             "config": {"workload": "QC verification: committee=%d, %d QCs x %d votes = %d votes (BASELINE config[%d]); QC::digest on GPU, "
                                    "verify_batch condition per vote, all-gather of accept bitmaps, per-QC AND" % (
-                                       args.committee, args.qcs, args.votes_per_qc, n, 2 if args.committee <= 1000 else 3),
-                       "votes": n, "shard": "contiguous ranges of %d votes per rank" % per, "window_bits": {"key": wa, "base": wb},
-                       "collective": "none (1 rank)" if world == 1 else ("fused peer-store all-gather (NVLink P2P)" if pag is not None else "ncclAllGather"),
-                       "l2": "per-key tables (%d keys) far larger than L2; inputs %.0f MB" % (args.committee, n * 72 / 1e6)}}))
+                                       args.committee, args.qcs, args.votes_per_qc, r["votes"], 2 if args.committee <= 1000 else 3),
+                       "votes": r["votes"], "shard": "contiguous ranges of %d votes per rank" % r["votes_per_rank"], "window_bits": r["window_bits"],
+                       "collective": r["collective"],
+                       "l2": "per-key tables (%d keys) far larger than L2; inputs %.0f MB" % (args.committee, r["votes"] * 72 / 1e6)}}))
     if world > 1:
         dist.destroy_process_group()
     eng.close()
@@ -358,6 +361,10 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-rank accept bitmaps reach every rank.  peer: the verify finish kernel stores its words straight "
                          "into every rank's buffer over NVLink (fused all-gather, hs_peer_*).  nccl: ncclAllGather after the kernel (baseline)")
+    ap.add_argument("--base-window", type=int, default=26,
+                    help="comb window of the base-point table in bits: 26 = 10 windows in 32 GB of HBM (this bench's choice: the tables of "
+                         "4,096 keys + 32 GB still fit in 180 GB), 24 = the library default (11 windows, 8.9 GB)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling QC leg (BASELINE config[3]) reported next to the headline")
     ap.add_argument("--committee", type=int, default=1000)
     ap.add_argument("--qcs", type=int, default=10000)
     ap.add_argument("--votes-per-qc", type=int, default=100)
@@ -381,9 +388,9 @@ def main():
     from hotstuff_b200 import Engine, build
     if not os.environ.get("HS_CRYPTO_LIB"):
         build.build_engine()
-    eng = Engine(local_rank, key_cache=(args.key_mode != "generic"))
+    eng = Engine(local_rank, key_cache=(args.key_mode != "generic"), base_window=args.base_window)
     n, L = args.n, args.msg_len
-    inp = make_inputs(n, args.keys, L, seed=1234 + rank, corrupt_frac=0.01)
+    inp = make_inputs(n, args.keys, L, seed=1234 + rank, corrupt_frac=0.01, engine=eng)
     n_bad = int(inp["corrupted"].sum())
 
     # ---- resident buffers
@@ -479,6 +486,20 @@ def main():
         torch.cuda.synchronize()
         kern.append(k0.elapsed_time(k1))
     kern_ms = float(np.median(kern))
+    # the dominant kernel alone: CUDA events recorded by the engine around k_verify_main<committee> on the stream it is launched on
+    main_ms = None
+    if args.key_mode != "generic" and eng.lib.hs_profile_enable(eng.h, 1) == 0:
+        ms_ = []
+        for _ in range(5):
+            if indexed:
+                eng.verify_committee_dev(d_vidx, d_sig, d_digest, d_bitmap, n, d_midx=d_arange)
+            else:
+                eng.verify_rec128_dev(d_recs, d_bitmap, n)
+            ms_.append(float(eng.lib.hs_profile_main_ms(eng.h)))
+        eng.lib.hs_profile_enable(eng.h, 0)
+        main_ms = float(np.median(ms_[1:]))
+    head_wa, head_wb = eng.window_bits
+    head_cached = eng.cached_keys
     dig = []
     for _ in range(3):   # the Digest kernel on its own (same stream, CUDA events)
         k0.record()
@@ -537,6 +558,11 @@ def main():
         cpu = {"value": m / dt, "unit": "verifies/s", "cores": cores, "kind": "port",
                "sample": "first %d records of the same workload: Digest(512 B) + verify_strict, %d pthreads, %.2f s" % (m, cores, dt)}
 
+    # ---- strong-scaling leg next to the weak headline: BASELINE config[3] (committee 10,000, 150 QCs x 6,667 votes = 1 M votes in
+    # total, sharded across the ranks, every rank ends with every verdict).  Re-registers the committee (untimed, epoch set-up).
+    strong = None
+    if not args.no_strong:
+        strong = qc_leg(eng, torch, dist, dev, rank, world, 10000, 150, 6667, max(5, args.steps), args.warmup, args.collective)
     if rank == 0:
         peaks = {}
         try:
@@ -544,48 +570,58 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = ALGO_BYTES_VERIFY * n / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        try:  # dram__bytes_read+write of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = tr.get("k_verify_main_bytes_per_record", 0) * n or None
+        dom_ms = main_ms if main_ms and main_ms > 0 else kern_ms
+        achieved = ALGO_BYTES_VERIFY * n / (dom_ms * 1e-3) / 1e9
+        # dram__bytes_read + dram__bytes_write and pipe utilisation of the kernels from THIS round's ncu --set full capture at the same
+        # 2^20 records per launch (tools/r2_pass2.sh -> tools/ncu_traffic.py -> profiles/r02_traffic.json); not measured in this run
+        tr = {}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         except Exception:
             pass
-        wa, wb = eng.window_bits
+        traffic = (tr.get("k_verify_main_bytes_per_record", 0) * n) or None
+        wa, wb = head_wa, head_wb
 
         def ndig(w):
             r = 253 % w
             return (253 + w - 1) // w + (1 if r in (0, w - 1) else 0)
         adds = (ndig(wa) if wa else 64) + ndig(wb)
-        # wide multiplies (IMAD.WIDE.U32[.X]) per verify: 7 field multiplications x 71 per mixed addition (SASS count of the hot
-        # loop), + ~0.7 k for the mod-l reduction and the batched-inversion share; generic keys add 252 doublings + decompression
-        wide_per_verify = adds * 7 * 71 + 700 + (0 if wa else 252 * 7 * 56 + 20000)
-        # field multiplications per verify (squarings counted as 0.7): 7 per mixed addition + mod-l/compare overhead + inversion share;
-        # generic keys: + 252 doublings (3 M + 4 S) + 64 additions (8 M) + decompression (~254 S + 20 M)
-        fe_muls = adds * 7 + 10 + (0 if wa else 252 * (3 + 4 * 0.7) + 64 * 8 + 254 * 0.7 + 20)
+        # SASS counts of the hot loop (tools/sass_hist.py, profiles/r02_sass_mainloop.txt): per mixed addition 336 IMAD.WIDE.U32.X (carry-in form,
+        # measured issue rate 32 lanes/clk/SM) + 171 IMAD.WIDE.U32 (54 lanes/clk/SM) + 129 other FMA-pipe instructions (64 lanes/clk/SM)
+        fma_clk_per_add = 336 / 32.0 + 171 / 54.0 + 129 / 64.0          # SM-clocks of FMA-pipe time per mixed addition per lane-group
         sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-        wide_rate = wide_per_verify * n / (kern_ms * 1e-3) / (148 * sm_clk * 1e6)
+        fma_floor_ms = adds * fma_clk_per_add * n / (148 * sm_clk * 1e6) * 1e3 if wa else None
+        fe_muls = adds * 7 + 10 + (0 if wa else 252 * (3 + 4 * 0.7) + 64 * 8 + 254 * 0.7 + 20)
         line = {
             "metric": "Ed25519 verifies/s", "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic", "config": workload_config(args, world), "gpu_launches": int(launches), "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>", "cached_keys": eng.cached_keys,
+            "roofline": {"bound": "hbm", "kernel": "k_verify_main<committee>" if args.key_mode != "generic" else "k_verify_main<generic>", "cached_keys": head_cached,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s", "traffic": traffic,
+                         "traffic_source": "profiles/r02_traffic.json: ncu --set full of this round at 2^20 records per launch (dram__bytes_read.sum + dram__bytes_write.sum); "
+                                           "table gathers, by design ~41x the algorithmic bytes" if traffic else None,
+                         "kernel_ms": dom_ms, "kernel_ms_covers": "k_verify_main<committee> alone (CUDA events recorded by the engine on its launch stream)" if main_ms else
+                                                                    "lookup + main + finish kernels of one verify pass",
+                         "verify_pass_ms": kern_ms, "verify_pass_covers": "lookup + main + finish kernels over 2^20 resident records",
                          "digest_kernel_ms": dig_ms, "digest_algorithmic_GBps": ALGO_BYTES_DIGEST * n / (dig_ms * 1e-3) / 1e9,
-                         "kernel_ms": kern_ms, "kernel_ms_covers": "lookup + main + finish kernels of one verify pass over 2^20 resident records",
+                         "digest_alu_pipe_pct_ncu": tr.get("k_digest32_fixed_alu_pipe_pct"),
                          "algorithmic_bytes_per_verify": ALGO_BYTES_VERIFY,
-                         "note": "integer-ALU bound path: 128 B of compulsory I/O per ~0.1-0.3 M INT32 instructions; HBM fraction is necessarily << 1 (SURVEY §0.7)"},
-            "alu_roofline": {"bound": "integer-multiply (FMA-heavy / IMAD) pipe — the resource that actually binds this path",
-                             "unit": "GF(2^255-19) multiplications/s", "achieved": fe_muls * n / (kern_ms * 1e-3), "peak": 1.044e11,
-                             "frac": fe_muls * n / (kern_ms * 1e-3) / 1.044e11, "field_muls_per_verify": fe_muls,
-                             "mixed_additions_per_verify": adds, "window_bits": {"key": wa, "base": wb},
-                             "wide_mads_per_clk_per_sm": wide_rate, "wide_mad_peak_per_clk_per_sm": 54.0,
-                             "ncu_fmaheavy_pipe_busy": 0.80,
-                             "peak_source": "fe_mul microbenchmark on this GPU (tools/microbench/febench.cu, profiles/r01_febench.txt); pipe utilisation from "
-                                            "ncu sm__pipe_fmaheavy_cycles_active (profiles/r01_ncu_summary.md); IMAD.WIDE peak from profiles/r01_pipes.txt"},
+                         "note": "integer-ALU bound path: 128 B of compulsory I/O per ~30 k INT32 instructions; the HBM fraction is necessarily << 1 (SURVEY §0.7): "
+                                 "see alu_roofline for the resource that binds"},
+            "alu_roofline": {"bound": "integer-multiply (FMA-heavy / IMAD) pipe — the resource that actually binds k_verify_main",
+                             "fmaheavy_pipe_busy_pct_ncu": tr.get("k_verify_main_fmaheavy_pipe_pct"),
+                             "fmaheavy_source": "profiles/r02_traffic.json (sm__pipe_fmaheavy_cycles_active, this round's ncu capture at 2^20 records)",
+                             "issue_floor_ms": fma_floor_ms, "issue_floor_frac": (fma_floor_ms / dom_ms) if fma_floor_ms else None,
+                             "issue_floor_basis": "mixed additions x (336 IMAD.WIDE.X / 32 + 171 IMAD.WIDE / 54 + 129 other / 64 lanes per clk per SM): raw issue "
+                                                  "rates from profiles/r01_pipes.txt and r01_widex.txt, instruction counts from profiles/r02_sass_mainloop.txt",
+                             "field_muls_per_s": fe_muls * n / (dom_ms * 1e-3), "field_mul_microbench_peak": 1.138e11,
+                             "field_mul_frac": fe_muls * n / (dom_ms * 1e-3) / 1.138e11,
+                             "field_mul_peak_source": "best fe_mul rate of tools/microbench/febench.cu on this GPU (profiles/r01_febench.txt, 2,048 threads/SM)",
+                             "field_muls_per_verify": fe_muls, "mixed_additions_per_verify": adds, "window_bits": {"key": wa, "base": wb}},
             "cpu_baseline": cpu,
+            "strong_scaling_config3": strong,
         }
         print(json.dumps(line))
     if world > 1:

@@ -15,6 +15,8 @@ SIGNATURES = {
     "hs_kernel_launches": (c_u64, [c_void_p]),
     "hs_cached_keys": (c_size_t, [c_void_p]),
     "hs_window_bits": (None, [c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "hs_profile_enable": (c_int, [c_void_p, c_int]),
+    "hs_profile_main_ms": (ctypes.c_double, [c_void_p]),
     "hs_host_alloc": (c_void_p, [c_size_t]),
     "hs_host_free": (None, [c_void_p]),
     "hs_verify_strict_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -38,6 +40,10 @@ SIGNATURES = {
     "hs_verify_committee_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_u32, c_void_p, c_void_p]),
     "hs_digest32_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "hs_digest32_fixed_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "hs_keygen_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hs_sign_digests": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hs_keygen_batch_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_sign_digests_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "hs_peer_setup": (c_int, [c_void_p, c_int, c_int, c_size_t, c_void_p]),
     "hs_peer_open": (c_int, [c_void_p, c_int, c_void_p]),
     "hs_peer_next": (c_int, [c_void_p, c_size_t, c_u32]),

@@ -696,6 +696,42 @@ __global__ void __launch_bounds__(HS_THREADS) k_tc_digests(const uint64_t *__res
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// ------------------------------------------------------------------------------------------------ load generation: keygen / sign
+// RFC 8032 key generation and signing of 32-byte digests (verify_core.cuh: keygen_core / sign_digest_core).  Not on the node's
+// path (the reference signs one message per request on the CPU); used to synthesise benchmark and test inputs.
+__global__ void __launch_bounds__(HS_THREADS) k_keygen(const uint8_t *__restrict__ seeds, size_t n, const ge_niels *__restrict__ btable,
+                                                        const comb_params cp, uint8_t *__restrict__ pks) {
+  __shared__ int32_t digits_s[HS_MAX_DIGITS * HS_THREADS];
+  const size_t i = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  uint32_t sd[8], A[8];
+  load32(sd, seeds + i * 32);
+  keygen_core(A, sd, btable, digits_s + threadIdx.x, HS_THREADS, cp);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(pks + i * 32);
+#pragma unroll
+  for (int j = 0; j < 8; j++) dst[j] = A[j];
+}
+__global__ void __launch_bounds__(HS_THREADS) k_sign_digests(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pks,
+                                                              const uint32_t *__restrict__ key_idx, const uint8_t *__restrict__ digests, size_t n,
+                                                              size_t n_keys, const ge_niels *__restrict__ btable, const comb_params cp,
+                                                              uint8_t *__restrict__ sig) {
+  __shared__ int32_t digits_s[HS_MAX_DIGITS * HS_THREADS];
+  const size_t i = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = key_idx ? key_idx[i] : (uint32_t)i;
+  if (k >= n_keys) k = 0;
+  uint32_t sd[8], A[8], M[8], R[8], S[8];
+  load32(sd, seeds + (size_t)k * 32);
+  load32(A, pks + (size_t)k * 32);
+  load32(M, digests + i * 32);
+  sign_digest_core(R, S, sd, A, M, btable, digits_s + threadIdx.x, HS_THREADS, cp);
+  uint4 *dst = reinterpret_cast<uint4 *>(sig + i * 64);
+  dst[0] = make_uint4(R[0], R[1], R[2], R[3]);
+  dst[1] = make_uint4(R[4], R[5], R[6], R[7]);
+  dst[2] = make_uint4(S[0], S[1], S[2], S[3]);
+  dst[3] = make_uint4(S[4], S[5], S[6], S[7]);
+}
+
 // ================================================================================================ host side
 struct dev_buf {
   void *p = nullptr;
@@ -751,6 +787,9 @@ struct hs_ctx {
   uint32_t *d_small_counter = nullptr;
   uint32_t small_seq = 0;
   bool small_enabled = true;
+  // optional timing of the dominant kernel alone (bench.py's roofline): events around k_verify_main<committee>
+  bool profile_main = false;
+  cudaEvent_t ev_prof[2] = {nullptr, nullptr};
   std::atomic<uint64_t> launches{0};
   std::mutex mu;
   std::mutex err_mu;                  // guards err only: fail() is also reached from argument checks taken before `mu`
@@ -996,7 +1035,9 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
       HS_CUDA(c, cudaGetLastError());
       HS_CUDA(c, cudaEventRecord(c->ev_side[1], c->stream_side));
     }
+    if (c->profile_main) HS_CUDA(c, cudaEventRecord(c->ev_prof[0], stream));
     k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
+    if (c->profile_main) HS_CUDA(c, cudaEventRecord(c->ev_prof[1], stream));
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
     if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_side[1], 0));
@@ -1109,7 +1150,7 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   if (!out) return HS_ERR_ARG;
   int wb = (int)(flags & 0xffu);
   if (wb == 0) wb = 24;  // 11 windows x 2^23 entries x 96 B = 8.9 GB of HBM for 11 instead of 16+ additions per [S]B
-  if (wb < 8 || wb > 24 || (wb % 2)) return HS_ERR_ARG;
+  if (wb < 8 || wb > 26 || (wb % 2)) return HS_ERR_ARG;  // 26 bits: 10 windows, 32 GB — one addition fewer per verify than the 8.9 GB default
   *out = nullptr;
   hs_ctx *c = new (std::nothrow) hs_ctx();
   if (!c) return HS_ERR_NOMEM;
@@ -1177,6 +1218,8 @@ void hs_ctx_destroy(hs_ctx *c) {
   if (c->h_learn_n) cudaFreeHost(c->h_learn_n);
   if (c->h_miss_total) cudaFreeHost(c->h_miss_total);
   if (c->ev_learn) cudaEventDestroy(c->ev_learn);
+  for (int i = 0; i < 2; i++)
+    if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
   for (int p = 0; p < HS_MAX_PEERS; p++)
     if (c->peer_mapped[p]) cudaIpcCloseMemHandle(c->peer_mapped[p]);
   cudaFree(c->peer_own);
@@ -1198,6 +1241,25 @@ void hs_window_bits(const hs_ctx *c, int *key_bits, int *base_bits) {
   if (base_bits) *base_bits = c ? c->cp.wb : 0;
 }
 uint64_t hs_kernel_launches(const hs_ctx *c) { return c ? c->launches.load() : 0; }
+/* Measurement hook: with profiling on, CUDA events bracket the k_verify_main<committee> launch of every verify pass on the stream the
+ * pass runs on; hs_profile_main_ms() waits for the last pass and returns that kernel's duration in ms (< 0: nothing recorded). */
+int hs_profile_enable(hs_ctx *c, int on) {
+  if (!c) return HS_ERR_ARG;
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  for (int i = 0; i < 2 && on; i++)
+    if (!c->ev_prof[i]) HS_CUDA(c, cudaEventCreate(&c->ev_prof[i]));
+  c->profile_main = on != 0;
+  return HS_OK;
+}
+double hs_profile_main_ms(hs_ctx *c) {
+  if (!c || !c->ev_prof[1]) return -1.0;
+  cudaSetDevice(c->device);
+  if (cudaEventSynchronize(c->ev_prof[1]) != cudaSuccess) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->ev_prof[0], c->ev_prof[1]) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
 
 void *hs_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -1585,13 +1647,82 @@ int hs_verify_groups(hs_ctx *c, const uint8_t *preimages, const uint64_t *pre_of
   return HS_OK;
 }
 
+// ---- load generation: RFC 8032 keygen / signing of 32-byte digests on the GPU
+int hs_keygen_batch_dev(hs_ctx *c, const void *d_seeds, size_t n, void *d_pks, void *stream) {
+  if (!c || (n && (!d_seeds || !d_pks))) return fail(c, HS_ERR_ARG, "hs_keygen_batch_dev: bad argument");
+  if (n == 0) return HS_OK;
+  HS_CUDA(c, cudaSetDevice(c->device));
+  k_keygen<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_seeds, n, c->d_btable, c->cp, (uint8_t *)d_pks);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+int hs_sign_digests_dev(hs_ctx *c, const void *d_seeds, const void *d_pks, size_t n_keys, const void *d_key_idx, const void *d_digests, size_t n,
+                        void *d_sig, void *stream) {
+  if (!c || (n && (!d_seeds || !d_pks || !d_digests || !d_sig || n_keys == 0)) || (!d_key_idx && n > n_keys))
+    return fail(c, HS_ERR_ARG, "hs_sign_digests_dev: bad argument");
+  if (n == 0) return HS_OK;
+  HS_CUDA(c, cudaSetDevice(c->device));
+  k_sign_digests<<<blocks_for(n), HS_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t *)d_seeds, (const uint8_t *)d_pks, (const uint32_t *)d_key_idx,
+                                                                          (const uint8_t *)d_digests, n, n_keys, c->d_btable, c->cp, (uint8_t *)d_sig);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
+  return HS_OK;
+}
+int hs_keygen_batch(hs_ctx *c, const uint8_t *seeds, size_t n, uint8_t *out_pks) {
+  if (!c || (n && (!seeds || !out_pks))) return fail(c, HS_ERR_ARG, "hs_keygen_batch: bad argument");
+  if (n == 0) return HS_OK;
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  HS_TRY(ensure(c, c->in[0], n * 32));
+  HS_TRY(ensure(c, c->out, n * 32));
+  HS_CUDA(c, cudaMemcpyAsync(c->in[0].p, seeds, n * 32, cudaMemcpyHostToDevice, c->stream));
+  HS_TRY(hs_keygen_batch_dev(c, c->in[0].p, n, c->out.p, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out_pks, c->out.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+int hs_sign_digests(hs_ctx *c, const uint8_t *seeds, const uint8_t *pks, size_t n_keys, const uint32_t *key_idx, const uint8_t *digests, size_t n,
+                    uint8_t *out_sig) {
+  if (!c || (n && (!seeds || !pks || !digests || !out_sig || n_keys == 0)) || (!key_idx && n > n_keys)) return fail(c, HS_ERR_ARG, "hs_sign_digests: bad argument");
+  if (n == 0) return HS_OK;
+  if (key_idx)
+    for (size_t i = 0; i < n; i++)
+      if (key_idx[i] >= n_keys) return fail(c, HS_ERR_ARG, "hs_sign_digests: key index out of range");
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  const size_t o_seed = 0, o_pk = n_keys * 32, o_ki = o_pk + n_keys * 32, o_d = o_ki + ((n * 4 + 15) & ~(size_t)15), total = o_d + n * 32;
+  HS_TRY(ensure(c, c->in[0], total));
+  HS_TRY(ensure(c, c->out, n * 64));
+  uint8_t *d = (uint8_t *)c->in[0].p;
+  HS_CUDA(c, cudaMemcpyAsync(d + o_seed, seeds, n_keys * 32, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_pk, pks, n_keys * 32, cudaMemcpyHostToDevice, c->stream));
+  if (key_idx) HS_CUDA(c, cudaMemcpyAsync(d + o_ki, key_idx, n * 4, cudaMemcpyHostToDevice, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(d + o_d, digests, n * 32, cudaMemcpyHostToDevice, c->stream));
+  HS_TRY(hs_sign_digests_dev(c, d + o_seed, d + o_pk, n_keys, key_idx ? d + o_ki : nullptr, d + o_d, n, c->out.p, c->stream));
+  HS_CUDA(c, cudaMemcpyAsync(out_sig, c->out.p, n * 64, cudaMemcpyDeviceToHost, c->stream));
+  HS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HS_OK;
+}
+
 // ---- multi-GPU peer routing (one process per GPU; handles are exchanged by the host, e.g. torch.distributed.all_gather_object)
 int hs_peer_setup(hs_ctx *c, int rank, int world, size_t total_words, uint8_t handle_out[64]) {
   if (!c || world < 1 || world > HS_MAX_PEERS || rank < 0 || rank >= world || !handle_out || total_words % (size_t)world)
     return fail(c, HS_ERR_ARG, "hs_peer_setup: bad argument (total_words must be a multiple of world)");
   std::lock_guard<std::mutex> g(c->mu);
   HS_CUDA(c, cudaSetDevice(c->device));
-  if (c->peer_own) return fail(c, HS_ERR_ARG, "hs_peer_setup: already set up");
+  if (c->peer_own) {  // a new geometry (another workload): drop the old buffers.  Every rank must have drained its stream first.
+    HS_CUDA(c, cudaDeviceSynchronize());
+    for (int p = 0; p < HS_MAX_PEERS; p++)
+      if (c->peer_mapped[p]) {
+        cudaIpcCloseMemHandle(c->peer_mapped[p]);
+        c->peer_mapped[p] = nullptr;
+      }
+    cudaFree(c->peer_own);
+    c->peer_own = nullptr;
+    c->peer_epoch = 0;
+    c->peer_armed = false;
+  }
   const size_t bytes = (2 * total_words + HS_MAX_PEERS + 16) * 4;
   HS_CUDA(c, cudaMalloc(&c->peer_own, bytes));
   HS_CUDA(c, cudaMemset(c->peer_own, 0, bytes));

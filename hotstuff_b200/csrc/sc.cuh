@@ -154,7 +154,7 @@ HS_HD void sc_bias_rt(uint32_t (&b)[9], int W) {
     b[bit >> 5] |= 1u << (bit & 31);
   }
 }
-// dig[i * stride] = signed digit i of s in radix 2^W (i < n), each in [-2^(W-1), 2^(W-1) - 1]; W <= 24
+// dig[i * stride] = signed digit i of s in radix 2^W (i < n), each in [-2^(W-1), 2^(W-1) - 1]; W <= 26 (hostemu checks every width 8 .. 26)
 HS_HD void sc_digits_rt(int32_t *dig, int stride, const uint32_t (&s)[8], const uint32_t (&bias)[9], int W, int n) {
   uint32_t u[9];
   uint64_t acc = 0;

@@ -366,3 +366,108 @@ HS_HD void comb_build_block(ge_niels *table, const ge_ext &P, int W, int win, in
     slot[c] = q;
   }
 }
+
+// ---- signing (load generation only: SURVEY §8f.4 — the reference node signs on the CPU, one signature per request,
+// crypto/src/lib.rs:185-191; this exists to synthesise 2^20-scale benchmark / test inputs in milliseconds).  RFC 8032 §5.1.6:
+//   (a, prefix) = clamp / split of SHA-512(seed);  r = SHA-512(prefix || M) mod l;  R = [r]B;  k = SHA-512(R || A || M) mod l;
+//   S = (r + k a) mod l.   M is a 32-byte Digest.  Deterministic: byte-identical to dalek / OpenSSL / the oracle.
+HS_HD void ge_compress_words(uint32_t (&out)[8], const ge_ext &p) {
+  fe zinv, x, y;
+  fe_invert(zinv, p.Z);
+  fe_mul(x, p.X, zinv);
+  fe_mul(y, p.Y, zinv);
+  fe_canon(x, x);
+  fe_canon(y, y);
+  for (int i = 0; i < 8; i++) out[i] = y.v[i];
+  out[7] |= (x.v[0] & 1u) << 31;
+}
+// r (8 limbs) + k (8 limbs) * a (8 limbs), reduced mod l.  a < 2^255, k < l, r < l: the 512-bit intermediate cannot overflow.
+HS_HD void sc_muladd(uint32_t (&out)[8], const uint32_t (&k)[8], const uint32_t (&a)[8], const uint32_t (&r)[8]) {
+  uint32_t t[16];
+  for (int i = 0; i < 16; i++) t[i] = (i < 8) ? r[i] : 0u;
+  for (int i = 0; i < 8; i++) {
+    uint64_t carry = 0;
+    for (int j = 0; j < 8; j++) {
+      uint64_t v = (uint64_t)k[i] * a[j] + t[i + j] + carry;
+      t[i + j] = (uint32_t)v;
+      carry = v >> 32;
+    }
+    for (int j = i + 8; j < 16 && carry; j++) {
+      uint64_t v = (uint64_t)t[j] + carry;
+      t[j] = (uint32_t)v;
+      carry = v >> 32;
+    }
+  }
+  sc_reduce512(out, t);
+}
+HS_HD void sha512_two_words32(uint32_t (&out)[16], const uint32_t (&p)[8], const uint32_t (&q)[8]) {  // SHA-512(p[32] || q[32])
+  uint64_t w[16];
+  for (int i = 0; i < 4; i++) {
+    w[i] = be64_from_le32(p[2 * i], p[2 * i + 1]);
+    w[4 + i] = be64_from_le32(q[2 * i], q[2 * i + 1]);
+  }
+  w[8] = 0x8000000000000000ULL;
+  for (int i = 9; i < 15; i++) w[i] = 0;
+  w[15] = 64 * 8;
+  sha512_state s;
+  sha512_init(s);
+  sha512_compress(s, w);
+  sha512_output_words(s, out);
+}
+// dig: na/nb scratch digit slots as in the verify paths.  sig_r / sig_s receive the two halves of the signature.
+HS_HD void sign_digest_core(uint32_t (&sig_r)[8], uint32_t (&sig_s)[8], const uint32_t (&seed)[8], const uint32_t (&A)[8], const uint32_t (&M)[8],
+                            const ge_niels *btable, int32_t *dig, int dig_stride, const comb_params &cp) {
+  uint32_t h[16], a[8], prefix[8], r[8], k[8];
+  {  // SHA-512(seed): one block of 32 bytes
+    uint64_t w[16];
+    for (int i = 0; i < 4; i++) w[i] = be64_from_le32(seed[2 * i], seed[2 * i + 1]);
+    w[4] = 0x8000000000000000ULL;
+    for (int i = 5; i < 15; i++) w[i] = 0;
+    w[15] = 32 * 8;
+    sha512_state s;
+    sha512_init(s);
+    sha512_compress(s, w);
+    sha512_output_words(s, h);
+  }
+  for (int i = 0; i < 8; i++) {
+    a[i] = h[i];
+    prefix[i] = h[8 + i];
+  }
+  a[0] &= 0xfffffff8u;                  // clamp: clear the low 3 bits, clear bit 255, set bit 254
+  a[7] = (a[7] & 0x7fffffffu) | 0x40000000u;
+  sha512_two_words32(h, prefix, M);
+  sc_reduce512(r, h);
+  ge_ext Rp;
+  ge_identity(Rp);
+  sc_digits_rt(dig, dig_stride, r, cp.bias_b, cp.wb, cp.nb);
+  ge_comb_accumulate_rt(Rp, btable, dig, dig_stride, cp.wb, cp.nb);
+  ge_compress_words(sig_r, Rp);
+  sha512_ram32(h, sig_r, A, M);
+  sc_reduce512(k, h);
+  sc_muladd(sig_s, k, a, r);
+}
+// public key of a seed: A = [a]B
+HS_HD void keygen_core(uint32_t (&A)[8], const uint32_t (&seed)[8], const ge_niels *btable, int32_t *dig, int dig_stride, const comb_params &cp) {
+  uint32_t h[16], a[8];
+  uint64_t w[16];
+  for (int i = 0; i < 4; i++) w[i] = be64_from_le32(seed[2 * i], seed[2 * i + 1]);
+  w[4] = 0x8000000000000000ULL;
+  for (int i = 5; i < 15; i++) w[i] = 0;
+  w[15] = 32 * 8;
+  sha512_state s;
+  sha512_init(s);
+  sha512_compress(s, w);
+  sha512_output_words(s, h);
+  for (int i = 0; i < 8; i++) a[i] = h[i];
+  a[0] &= 0xfffffff8u;
+  a[7] = (a[7] & 0x7fffffffu) | 0x40000000u;
+  // the comb recoder takes scalars below 2^253: split a = a_lo + 2^252 * a_hi (a_hi in 4 .. 7) is avoided by reducing mod l first
+  uint32_t t[16], ar[8];
+  for (int i = 0; i < 16; i++) t[i] = (i < 8) ? a[i] : 0u;
+  sc_reduce512(ar, t);                  // [a]B = [a mod l]B
+  ge_ext P;
+  ge_identity(P);
+  sc_digits_rt(dig, dig_stride, ar, cp.bias_b, cp.wb, cp.nb);
+  ge_comb_accumulate_rt(P, btable, dig, dig_stride, cp.wb, cp.nb);
+  ge_compress_words(A, P);
+}

@@ -171,6 +171,24 @@ class Engine:
         out = bitmap_to_bools(gbm, n_groups)
         return (out, bitmap_to_bools(ibm, n)) if want_items else out
 
+    def keygen_batch(self, seeds):
+        """RFC 8032 public keys of n 32-byte seeds, computed on the GPU (load generation; hs_keygen_batch)."""
+        seeds = _u8(seeds, 32).reshape(-1, 32)
+        out = np.zeros_like(seeds)
+        self._check(self.lib.hs_keygen_batch(self.h, _ptr(seeds), seeds.shape[0], _ptr(out)), "hs_keygen_batch")
+        return out
+
+    def sign_digests(self, seeds, pks, digests, key_idx=None):
+        """RFC 8032 signatures over 32-byte digests, made on the GPU (load generation; hs_sign_digests)."""
+        seeds = _u8(seeds, 32).reshape(-1, 32)
+        pks = _u8(pks, 32).reshape(-1, 32)
+        digests = _u8(digests, 32).reshape(-1, 32)
+        ki = None if key_idx is None else np.ascontiguousarray(key_idx, dtype=np.uint32)
+        n = digests.shape[0]
+        out = np.zeros((n, 64), dtype=np.uint8)
+        self._check(self.lib.hs_sign_digests(self.h, _ptr(seeds), _ptr(pks), seeds.shape[0], _ptr(ki), _ptr(digests), n, _ptr(out)), "hs_sign_digests")
+        return out
+
     def committee_register(self, pks):
         pks = _u8(pks, 32).reshape(-1, 32)
         n = pks.shape[0]
@@ -254,6 +272,13 @@ class Engine:
     def qc_and_dev(self, d_vote_bitmap, d_qc_idx, n_votes, n_qc, d_qc_bitmap):
         self._check(self.lib.hs_qc_and_dev(self.h, d_vote_bitmap.data_ptr(), d_qc_idx.data_ptr(), n_votes, n_qc, d_qc_bitmap.data_ptr(), self._stream()),
                     "hs_qc_and_dev")
+
+    def keygen_batch_dev(self, d_seeds, d_pks, n):
+        self._check(self.lib.hs_keygen_batch_dev(self.h, d_seeds.data_ptr(), n, d_pks.data_ptr(), self._stream()), "hs_keygen_batch_dev")
+
+    def sign_digests_dev(self, d_seeds, d_pks, n_keys, d_digests, d_sig, n, d_key_idx=None):
+        self._check(self.lib.hs_sign_digests_dev(self.h, d_seeds.data_ptr(), d_pks.data_ptr(), n_keys, None if d_key_idx is None else d_key_idx.data_ptr(),
+                                                 d_digests.data_ptr(), n, d_sig.data_ptr(), self._stream()), "hs_sign_digests_dev")
 
     def digest32_fixed_dev(self, d_msgs, msg_len, d_out, n):
         self._check(self.lib.hs_digest32_fixed_dev(self.h, d_msgs.data_ptr(), msg_len, n, d_out.data_ptr(), self._stream()), "hs_digest32_fixed_dev")

@@ -56,6 +56,8 @@ class PeerAllGather:
         self.e, self.rank, self.world, self.n = engine, rank, world, n_total
         self.per_words = shard_range(n_total, 0, world)[2] // 32
         self.total_words = self.per_words * world
+        torch.cuda.synchronize()
+        dist.barrier()                      # a previous PeerAllGather on this engine is released by hs_peer_setup: nobody may still use it
         h = (ctypes.c_uint8 * 64)()
         ok = engine.lib.hs_peer_setup(engine.h, rank, world, self.total_words, h) == 0
         handles = [None] * world

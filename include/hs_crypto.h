@@ -52,7 +52,7 @@ typedef struct {
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
 /* device: CUDA ordinal.  Builds the base-point comb table on the GPU (default window 24 bits = 8.9 GB of HBM).
- * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..24), bits 8-15 = forced per-key window width
+ * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..26; 26 = 10 windows in 32 GB, one addition fewer per verify), bits 8-15 = forced per-key window width
  * (8..16; 0 = widest that fits ~62 % of device memory); HS_FLAG_NO_KEY_CACHE disables the key cache (also env HS_KEY_CACHE=0). */
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
@@ -69,6 +69,10 @@ size_t hs_cached_keys(const hs_ctx *ctx);
 void hs_window_bits(const hs_ctx *ctx, int *key_bits, int *base_bits);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t hs_kernel_launches(const hs_ctx *ctx);
+/* Measurement hook (bench.py's roofline): with profiling on, CUDA events bracket the k_verify_main<committee> launch of every
+ * verify pass, on the stream the pass runs on; hs_profile_main_ms() waits for the last pass and returns that kernel's duration. */
+int hs_profile_enable(hs_ctx *ctx, int on);
+double hs_profile_main_ms(hs_ctx *ctx);
 /* Pinned host memory helpers (optional; any host pointer is accepted by the host entry points). */
 void *hs_host_alloc(size_t bytes);
 void hs_host_free(void *p);
@@ -204,6 +208,17 @@ int hs_verify_qc_votes_dev(hs_ctx *ctx, const void *d_qc_digests, const void *d_
                            const void *d_qc_idx, size_t n_votes, void *d_vote_bitmap, void *stream);
 int hs_qc_and_dev(hs_ctx *ctx, const void *d_vote_bitmap, const void *d_qc_idx, size_t n_votes, size_t n_qc, void *d_qc_bitmap, void *stream);
 
+/* ---- load generation: RFC 8032 key generation and signing of 32-byte digests ON THE GPU ---------------------------------------
+ * generate_keypair / Signature::new (crypto/src/lib.rs:167-175,185-191) for input synthesis only: the node itself signs one
+ * message per request on the CPU (SignatureService) and keeps doing so.  Deterministic, byte-identical to dalek / OpenSSL.
+ * Signature i is over digests[i] with key key_idx[i] (NULL: key i).  Secret seeds travel to the device: test / benchmark use. */
+int hs_keygen_batch(hs_ctx *ctx, const uint8_t *seeds /* n x 32 */, size_t n, uint8_t *out_pks /* n x 32 */);
+int hs_sign_digests(hs_ctx *ctx, const uint8_t *seeds, const uint8_t *pks, size_t n_keys, const uint32_t *key_idx_or_null,
+                    const uint8_t *digests /* n x 32 */, size_t n, uint8_t *out_sig /* n x 64 */);
+int hs_keygen_batch_dev(hs_ctx *ctx, const void *d_seeds, size_t n, void *d_pks, void *stream);
+int hs_sign_digests_dev(hs_ctx *ctx, const void *d_seeds, const void *d_pks, size_t n_keys, const void *d_key_idx_or_null, const void *d_digests,
+                        size_t n, void *d_sig, void *stream);
+
 /* ---- multi-GPU: fused all-gather of the accept bitmap (one process per GPU, same node, NVLink) ------------------------
  * Each rank creates a result buffer for the GLOBAL bitmap (total_words) and exports a 64-byte CUDA-IPC handle; the host
  * exchanges handles (e.g. torch.distributed.all_gather_object) and opens every peer's.  hs_peer_next() then arms the next
@@ -213,7 +228,8 @@ int hs_qc_and_dev(hs_ctx *ctx, const void *d_vote_bitmap, const void *d_qc_idx, 
  * The buffer is double-buffered by epoch parity (hs_peer_bitmap() follows the most recently armed epoch): consume epoch e's
  * bitmap on the same stream before enqueueing the verify of epoch e+1 and no barrier between ranks is needed.  The flag
  * exchange runs inside the finish kernel (no extra launches).  total_words must be world x (words per rank); a peer that
- * never signals makes hs_peer_timed_out() return 1 and its shard read as all-rejected. */
+ * never signals makes hs_peer_timed_out() return 1 and its shard read as all-rejected.  hs_peer_setup may be called again
+ * (new total_words): the old buffers are released — every rank must have drained its stream and re-exchange handles. */
 int hs_peer_setup(hs_ctx *ctx, int rank, int world, size_t total_words, uint8_t handle_out[64]);
 int hs_peer_open(hs_ctx *ctx, int peer_rank, const uint8_t handle[64]);
 int hs_peer_next(hs_ctx *ctx, size_t word_offset, uint32_t epoch);

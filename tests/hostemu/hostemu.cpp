@@ -248,3 +248,17 @@ extern "C" void emu_sha512_padkw_path(const uint8_t *msg, uint64_t len, uint8_t 
   sha512_output_words(s, o);
   memcpy(out, o, 64);
 }
+
+// load-generation signer (sign_digest_core / keygen_core): must reproduce RFC 8032 signatures byte for byte
+extern "C" void emu_sign_digest(const uint8_t seed[32], const uint8_t msg32[32], uint8_t pk_out[32], uint8_t sig_out[64]) {
+  ensure_btable();
+  uint32_t sd[8], M[8], A[8], R[8], S[8];
+  load_words(sd, seed);
+  load_words(M, msg32);
+  int32_t dig[HS_MAX_DIGITS];
+  keygen_core(A, sd, g_btable.data(), dig, 1, g_cp);
+  sign_digest_core(R, S, sd, A, M, g_btable.data(), dig, 1, g_cp);
+  memcpy(pk_out, A, 32);
+  memcpy(sig_out, R, 32);
+  memcpy(sig_out + 32, S, 32);
+}

@@ -246,7 +246,7 @@ def test_verify_msgs_chunked_pipeline(engine, oracle):
     assert (got == want).all()
 
 
-@pytest.mark.parametrize("base_window,key_window", [(8, 8), (12, 10), (16, 12), (20, 14), (24, 16), (24, 15), (24, 13), (24, 14), (24, 9), (24, 11), (22, 12)])
+@pytest.mark.parametrize("base_window,key_window", [(8, 8), (12, 10), (16, 12), (20, 14), (24, 16), (24, 15), (24, 13), (24, 14), (24, 9), (24, 11), (22, 12), (26, 15)])
 def test_window_width_independence(oracle, golden, base_window, key_window):
     """Verdicts must not depend on the comb window widths (table sizes): golden vectors + a random set + the randomised
     adversarial set, through the generic, lookup, indexed and hs_verify_qcs paths — for the small / medium table geometries AND
@@ -643,3 +643,24 @@ def test_fixed_length_digest_kernel_shapes(engine, oracle):
         sig[::11, 20] ^= 2
         want = oracle.verify_rec128(np.concatenate([sig, pks[kidx], d], axis=1))
         assert (engine.verify_msgs(sig, msgs.reshape(-1), L, pk=pks[kidx]) == want).all(), (L, n)
+
+
+def test_gpu_signer_is_byte_identical_to_rfc8032(engine, oracle, golden):
+    """hs_keygen_batch / hs_sign_digests (load generation): deterministic RFC 8032 output, byte for byte the oracle's (which is
+    pinned on the RFC 8032 KATs and OpenSSL), including the reference's keys() and its "Hello, world!" signature."""
+    r = golden["reference"]
+    seeds = np.array([np.frombuffer(bytes.fromhex(s), np.uint8) for s in r["seeds"]])
+    pks = engine.keygen_batch(seeds)
+    assert [p.tobytes().hex() for p in pks] == r["pks"]
+    hello = np.frombuffer(bytes.fromhex(r["hello_digest"]), np.uint8).reshape(1, 32)
+    assert engine.sign_digests(seeds, pks, hello, key_idx=[3])[0].tobytes().hex() == r["hello_sig_key3"]
+    rng = np.random.default_rng(99)
+    n, nk = 5000, 300
+    sd = rng.integers(0, 256, (nk, 32), dtype=np.uint8)
+    pk = engine.keygen_batch(sd)
+    assert (pk == oracle.keygen_batch(sd)).all()
+    ki = rng.integers(0, nk, n).astype(np.uint32)
+    dg = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    sig = engine.sign_digests(sd, pk, dg, key_idx=ki)
+    assert (sig == oracle.sign_batch(sd, pk, ki, dg.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)).all()
+    assert engine.verify_rec128(np.concatenate([sig, pk[ki], dg], axis=1)).all()

@@ -147,3 +147,24 @@ def test_randomised_adversarial_differential_hostemu(hostemu, oracle):
         assert hostemu.emu_verify_generic(sig, pk, m, ctypes.c_uint64(32)) == want
         agree += 1
     assert agree == 600
+
+
+def test_load_generation_signer_matches_rfc8032(hostemu, oracle, golden):
+    """sign_digest_core / keygen_core (the GPU load-generation signer) under host emulation: byte-identical to the oracle's RFC 8032
+    signer (itself pinned on the RFC 8032 KATs and OpenSSL) for the reference's keys() seeds and random seeds, 32-byte digests."""
+    hostemu.emu_set_windows(10, 12)
+    rng = np.random.default_rng(8032)
+    seeds = [bytes.fromhex(s) for s in golden["reference"]["seeds"]] + [rng.bytes(32) for _ in range(40)]
+    for i, seed in enumerate(seeds):
+        m = oracle.digest32(b"msg" + bytes([i]))
+        pk, sig = ctypes.create_string_buffer(32), ctypes.create_string_buffer(64)
+        hostemu.emu_sign_digest(seed, m, pk, sig)
+        assert pk.raw == oracle.keygen(seed), i
+        assert sig.raw == oracle.sign(seed, m), i
+    assert golden["reference"]["hello_sig_key3"] == _emu_sign(hostemu, seeds[3], bytes.fromhex(golden["reference"]["hello_digest"]))
+
+
+def _emu_sign(hostemu, seed, m):
+    pk, sig = ctypes.create_string_buffer(32), ctypes.create_string_buffer(64)
+    hostemu.emu_sign_digest(seed, m, pk, sig)
+    return sig.raw.hex()

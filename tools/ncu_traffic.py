@@ -28,6 +28,11 @@ for r in rows[2:]:
     b = to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr])
     key = "k_verify_main" if "k_verify_main<(bool)1>" in name or "k_verify_main<1>" in name else name.split("(")[0].replace("void ", "")
     traffic[key + "_bytes_per_record"] = b / nrec
+    for short, metric in (("fmaheavy_pipe_pct", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+                          ("alu_pipe_pct", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed"), ("duration", "gpu__time_duration.sum")):
+        if metric in hdr:
+            traffic[key + "_" + short] = float(r[hdr.index(metric)].replace(",", ""))
+traffic["records_per_launch"] = nrec
 open(md, "w").write("\n".join(out) + "\n")
 json.dump(traffic, open(js, "w"), indent=1)
 print(json.dumps(traffic))
