@@ -361,9 +361,10 @@ def main():
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the per-rank accept bitmaps reach every rank.  peer: the verify finish kernel stores its words straight "
                          "into every rank's buffer over NVLink (fused all-gather, hs_peer_*).  nccl: ncclAllGather after the kernel (baseline)")
-    ap.add_argument("--base-window", type=int, default=26,
-                    help="comb window of the base-point table in bits: 26 = 10 windows in 32 GB of HBM (this bench's choice: the tables of "
-                         "4,096 keys + 32 GB still fit in 180 GB), 24 = the library default (11 windows, 8.9 GB)")
+    ap.add_argument("--base-window", type=int, default=24,
+                    help="comb window of the base-point table in bits: 24 = the library default (11 windows, 8.9 GB).  26 (10 windows, 32 GB: one "
+                         "mixed addition fewer) was measured on B200 and buys nothing — 2.361 vs 2.371 ms for the main kernel — because the gathers "
+                         "from the 3.6x larger table miss L2/TLB more often (profiles/r02_bench_base_window_26.json)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling QC leg (BASELINE config[3]) reported next to the headline")
     ap.add_argument("--committee", type=int, default=1000)
     ap.add_argument("--qcs", type=int, default=10000)
