@@ -167,7 +167,10 @@ template <bool COMMITTEE>
 #ifndef HS_MAIN_MINBLOCKS
 #define HS_MAIN_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : 3) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
+#ifndef HS_GENERIC_MINBLOCKS
+#define HS_GENERIC_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(HS_THREADS, COMMITTEE ? HS_MAIN_MINBLOCKS : HS_GENERIC_MINBLOCKS) k_verify_main(in_layout L, size_t n_arg, const uint32_t *__restrict__ n_ptr,
                                                              const uint32_t *__restrict__ index_list, const ge_niels *__restrict__ btable,
                                                              committee_tables C, main_out O, const comb_params cp) {
   // one buffer, two lives: record staging while loading, then the signed digits [digit][thread] (conflict-free columns)

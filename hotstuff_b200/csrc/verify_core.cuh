@@ -242,11 +242,17 @@ HS_HD void ge_scalarmult_window4(ge_ext &acc, const ge_ext &P, const uint32_t (&
 #endif
   for (int i = 0; i < 64; i++) {
     if (i != 0) {
-      ge_p1p1 c;
-      ge_dbl_p1p1(c, acc); ge_p1p1_to_proj(acc, c);
-      ge_dbl_p1p1(c, acc); ge_p1p1_to_proj(acc, c);
-      ge_dbl_p1p1(c, acc); ge_p1p1_to_proj(acc, c);
-      ge_dbl_p1p1(c, acc); ge_p1p1_to_ext(acc, c);
+      // ONE copy of the doubling in the instruction stream (the 4x unrolled form made this loop body 5.2 k instructions and the
+      // kernel's top stall "no instruction": profiles/r02_ncu_generic_before.txt); T is only needed after the last of the four
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int d = 0; d < 4; d++) {
+        ge_p1p1 c;
+        ge_dbl_p1p1(c, acc);
+        ge_p1p1_to_proj(acc, c);
+        if (d == 3) fe_mul(acc.T, c.E, c.H);
+      }
     }
     int d = ds.next();
     uint32_t neg = (uint32_t)(d < 0);
