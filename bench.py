@@ -437,6 +437,11 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
+    if args.key_mode == "cache":          # the cache learns at most 1,024 keys per call: warm up until every signer key has its table
+        for _ in range(16):
+            if eng.cached_keys >= args.keys:
+                break
+            step_resident()
     torch.cuda.synchronize()
     if world > 1:
         # every rank must hold every rank's verdicts: check this rank's slice of the gathered bitmap, and that the other

@@ -30,6 +30,8 @@
 #define HS_FINISH_GROUP 16  // signatures whose Z's share one inversion
 #define HS_NO_KEY 0xffffffffu
 #define HS_LEARN_MAX 8192u  // unknown keys examined per call
+#define HS_LEARN_PER_CALL 1024u  // new tables built per call at most (bounds the latency a flood of one-off keys can add to one call)
+#define HS_CACHE_RESET_MIN_CALLS 64u  // a full cache is cleared at most once per this many verify calls
 
 // ------------------------------------------------------------------------------------------------ input layout
 // One descriptor covers every caller-facing layout: packed hs_rec128 records, separate sig/pk arrays with
@@ -454,18 +456,20 @@ __device__ __forceinline__ void fe_load_global(fe &r, const fe *p) {
   uint4 a = s[0], b = s[1];
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
 }
-// One thread owns HS_FINISH_GROUP (16) consecutive records and a block owns 2,048.  Montgomery's trick at two levels so that ONE
+// One thread owns `group` (16, 8 or 4: fewer for small batches, so that enough blocks exist to hide the one serial field inversion
+// each block waits for — at 126 k records the 16-record form ran 62 blocks for 110 us) consecutive records.  Montgomery's trick at two levels so that ONE
 // field inversion per 64 records is executed (by warp 0, lane l inverting the product of threads 4l..4l+3) instead of one
 // per thread: phase A prefix products of the thread's 16 Z's; phase B the block-level inversion through shared memory;
 // phase C back-substitution + affine comparison with R's encoding.  Two neighbouring lanes combine their 16 verdicts into
 // one bitmap word, which goes to the local bitmap or — armed by hs_peer_next — straight into every peer's buffer, after
 // which the last block of the grid exchanges the epoch flags with the peers (no separate signal / wait launches).
 __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_t n, const fe *__restrict__ xyz, const uint8_t *__restrict__ meta,
-                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out, const peer_route P) {
+                                                               uint32_t mode, uint32_t *__restrict__ bitmap, uint8_t *flags_out, const peer_route P,
+                                                               const int group) {
   __shared__ fe tot[HS_THREADS];
   const size_t t = (size_t)blockIdx.x * HS_THREADS + threadIdx.x;
-  const size_t first = t * HS_FINISH_GROUP;
-  const int cnt = (first < n) ? (int)((n - first < HS_FINISH_GROUP) ? (n - first) : HS_FINISH_GROUP) : 0;
+  const size_t first = t * (size_t)group;
+  const int cnt = (first < n) ? (int)((n - first < (size_t)group) ? (n - first) : group) : 0;
   fe prod[HS_FINISH_GROUP];
   fe run;
   fe_set1(run);
@@ -523,14 +527,16 @@ __global__ void __launch_bounds__(HS_THREADS) k_verify_finish(in_layout L, size_
       if (ok) bits |= 1u << c;
     }
   }
-  // lanes 2j and 2j+1 hold bits [32j .. 32j+15] and [32j+16 .. 32j+31] of word (t/2)
-  const uint32_t other = __shfl_xor_sync(0xffffffffu, bits, 1);
-  if ((threadIdx.x & 1) == 0 && first < n) {
-    const uint32_t word = bits | (other << 16);
+  // 32 / group neighbouring lanes hold the verdicts of one bitmap word: butterfly-OR them together
+  const int lanes_per_word = 32 / group;
+  uint32_t word = bits << (group * (threadIdx.x & (lanes_per_word - 1)));
+  for (int m = 1; m < lanes_per_word; m <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, m);
+  if ((threadIdx.x & (lanes_per_word - 1)) == 0 && first < n) {
+    const size_t widx = t / lanes_per_word;
     if (P.n == 0) {
-      bitmap[t >> 1] = word;
+      bitmap[widx] = word;
     } else {
-      const size_t at = (P.epoch & 1u) * P.total_words + P.word_offset + (t >> 1);
+      const size_t at = (P.epoch & 1u) * P.total_words + P.word_offset + widx;
 #pragma unroll 1
       for (int p = 0; p < P.n; p++) P.buf[p][at] = word;  // fused all-gather: one NVLink store per peer
     }
@@ -773,6 +779,7 @@ struct hs_ctx {
   cudaEvent_t ev_learn = nullptr;
   bool learn_pending = false;
   bool cache_full = false;           // no free slot: only the miss RATE is watched (a mostly-missing full cache is reset)
+  uint64_t calls_since_reset = HS_CACHE_RESET_MIN_CALLS;
   size_t learn_records = 0;          // records of the pass whose misses are parked in h_learn_*
   uint32_t *h_miss_total = nullptr;  // pinned: total misses of that pass
   // multi-GPU peer routing
@@ -909,11 +916,13 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   if (!c->learn_pending) return HS_OK;
   if (cudaEventQuery(c->ev_learn) != cudaSuccess) return HS_OK;  // copy still in flight: try again on the next call
   c->learn_pending = false;
+  c->calls_since_reset++;
   if (!c->cache_enabled || c->explicit_committee) return HS_OK;
   if (c->cache_full) {
     // Full cache that no longer matches the traffic (e.g. the validator set rotated): more than half of the last pass missed.
     // Start over — the next passes relearn the keys that are actually in use.  (No per-key eviction)
-    if (c->learn_records >= 64 && (size_t)*c->h_miss_total * 2 > c->learn_records) {
+    if (c->learn_records >= 64 && (size_t)*c->h_miss_total * 2 > c->learn_records && c->calls_since_reset >= HS_CACHE_RESET_MIN_CALLS) {
+      c->calls_since_reset = 0;
       c->n_keys = 0;
       c->h_pks.clear();
       std::fill(c->h_slots.begin(), c->h_slots.end(), HS_NO_KEY);
@@ -931,7 +940,7 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   const size_t old_n = c->n_keys;
   size_t n_new = 0;
   const uint32_t mask = c->slot_mask;
-  for (uint32_t t = 0; t < got && old_n + n_new < c->cache_cap; t++) {
+  for (uint32_t t = 0; t < got && old_n + n_new < c->cache_cap && n_new < HS_LEARN_PER_CALL; t++) {
     const uint8_t *key = c->h_learn_keys + 32 * (size_t)t;
     uint32_t w[8];
     memcpy(w, key, 32);
@@ -957,8 +966,7 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
                                                                 c->d_atables + old_n * c->a_table_entries, c->d_key_flags + old_n);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
-  // h_pks / h_slots are pageable vectors that may reallocate on the next learn: make the uploads finish first
-  HS_CUDA(c, cudaStreamSynchronize(stream));
+  // (no synchronisation: copies from pageable memory return once the source is staged, so the host vectors may change afterwards)
   c->n_keys = old_n + n_new;
   if (c->n_keys >= c->cache_cap) c->cache_full = true;  // no free slot: unknown keys stay on the generic path until a reset
   return HS_OK;
@@ -1050,13 +1058,14 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
   }
-  const size_t fin_threads = (n + HS_FINISH_GROUP - 1) / HS_FINISH_GROUP;
+  const int fin_group = n >= (1u << 19) ? 16 : (n >= (1u << 18) ? 8 : 4);
+  const size_t fin_threads = (n + fin_group - 1) / fin_group;
   peer_route P{};
   if (c->peer_armed) {
     P = c->peers;
     c->peer_armed = false;
   }
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, d_flags_out, P);
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, d_flags_out, P, fin_group);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;
