@@ -760,7 +760,7 @@ struct hs_ctx {
     cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_done = nullptr;
   } lanes[2];
   cudaStream_t stream_dig = nullptr;          // high priority: Digest kernels of the chunks ahead (pipelined mode)
-  cudaEvent_t ev_in = nullptr, ev_dig[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_in = nullptr, ev_dig[16] = {};
   ge_niels *d_btable = nullptr;
   comb_params cp{};
   size_t a_table_entries = 0;
@@ -1186,7 +1186,7 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream_dig, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
-  for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_dig[i], cudaEventDisableTiming);
+  for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_dig[i], cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
@@ -1242,7 +1242,8 @@ void hs_ctx_destroy(hs_ctx *c) {
     if (V.side) cudaStreamDestroy(V.side);
     if (V.run) cudaStreamDestroy(V.run);
   }
-  for (cudaEvent_t ev : {c->ev_in, c->ev_dig[0], c->ev_dig[1], c->ev_dig[2], c->ev_dig[3]})
+  if (c->ev_in) cudaEventDestroy(c->ev_in);
+  for (cudaEvent_t ev : c->ev_dig)
     if (ev) cudaEventDestroy(ev);
   if (c->stream_dig) cudaStreamDestroy(c->stream_dig);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
@@ -1511,35 +1512,89 @@ int hs_digest32_fixed_dev(hs_ctx *c, const void *d_msgs, size_t msg_len, size_t 
   HS_CUDA(c, cudaSetDevice(c->device));
   return launch_digest_fixed(c, (const uint8_t *)d_msgs, msg_len, n, (uint32_t *)d_out, (cudaStream_t)stream);
 }
-// Large resident batches are cut into 2^17-record chunks that flow through three streams: the Digest kernel of chunk j+1 (ALU pipe:
-// funnel shifts / LOP3 / adds at 94 % utilisation) runs on a high-priority stream WHILE the verify kernels of chunk j (FMA-heavy pipe:
-// wide multiplies at 83 %) run on one of two lanes, and the latency-bound finish kernel of chunk j overlaps the main kernel of
-// chunk j+1 on the other lane.  The two dominant kernels bind different issue pipes, so sharing the SMs beats running them back to back.
-#define HS_PIPE_CHUNK ((size_t)1 << 17)
+// Large resident batches: the Digest kernel (ALU pipe: funnel shifts / LOP3 / adds, 94 % busy) and the verify main kernel
+// (FMA-heavy pipe: wide multiplies, 83 % busy) bind DIFFERENT issue pipes, so they are made to share the SMs instead of running back
+// to back: the messages are hashed in growing chunks on a high-priority stream while the main kernel of every chunk whose digests
+// are ready runs on the caller's stream.  One key lookup, one generic side pass (records with unregistered keys) and one finish
+// kernel serve the whole batch, exactly as in the single-pass form.
 #define HS_PIPE_MIN ((size_t)1 << 18)
+#define HS_PIPE_MAX_CHUNKS 16
 static int verify_msgs_pipelined(hs_ctx *c, const uint8_t *d_sig, const uint8_t *d_pk, const uint32_t *d_vidx, const uint8_t *d_msgs, size_t msg_len,
                                  size_t n, uint32_t mode, uint8_t *d_digests, uint32_t *d_bitmap, cudaStream_t stream) {
   const bool indexed = d_vidx != nullptr;
-  if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
-  if (!indexed) HS_TRY(learn_process(c, stream));  // tables of newly learned keys are built before any lane looks keys up
+  hs_ctx::verify_lane &V = c->lanes[0];
+  if (!indexed) HS_TRY(learn_process(c, stream));
+  HS_TRY(ensure(c, V.xyz, n * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, V.meta, n));
+  if (!indexed) {
+    HS_TRY(ensure(c, V.vidx, n * 4));
+    HS_TRY(ensure(c, V.miss, n * 4));
+  }
+  // chunk sizes: 2^16, 2^16, 2^17, 2^18, 2^18, ... — a short first chunk starts the verify kernels early, long later chunks keep whole waves
+  size_t lo_of[HS_PIPE_MAX_CHUNKS + 1];
+  int n_chunks = 0;
+  {
+    size_t lo = 0, sz = (size_t)1 << 16;
+    while (lo < n && n_chunks < HS_PIPE_MAX_CHUNKS - 1) {
+      lo_of[n_chunks++] = lo;
+      lo += sz;
+      if (n_chunks >= 2 && sz < ((size_t)1 << 18)) sz <<= 1;
+    }
+    if (lo < n) lo_of[n_chunks++] = lo;  // whatever is left goes into the last chunk
+    lo_of[n_chunks] = n;
+  }
   HS_CUDA(c, cudaEventRecord(c->ev_in, stream));
   HS_CUDA(c, cudaStreamWaitEvent(c->stream_dig, c->ev_in, 0));
-  for (hs_ctx::verify_lane &V : c->lanes) HS_CUDA(c, cudaStreamWaitEvent(V.run, c->ev_in, 0));
-  size_t j = 0;
-  for (size_t lo = 0; lo < n; lo += HS_PIPE_CHUNK, j++) {
-    const size_t cnt = (n - lo < HS_PIPE_CHUNK) ? (n - lo) : HS_PIPE_CHUNK;
+  for (int j = 0; j < n_chunks; j++) {
+    const size_t lo = lo_of[j], cnt = lo_of[j + 1] - lo;
     HS_TRY(launch_digest_fixed(c, d_msgs + lo * msg_len, msg_len, cnt, (uint32_t *)(d_digests + lo * 32), c->stream_dig));
-    HS_CUDA(c, cudaEventRecord(c->ev_dig[j & 3], c->stream_dig));
-    const int lane = (int)(j & 1);
-    hs_ctx::verify_lane &V = c->lanes[lane];
-    HS_CUDA(c, cudaStreamWaitEvent(V.run, c->ev_dig[j & 3], 0));
-    in_layout L{d_sig + lo * 64, 64, d_pk ? d_pk + lo * 32 : nullptr, 32, d_vidx ? d_vidx + lo : nullptr, d_digests + lo * 32, 32, nullptr, nullptr, 32, 0};
-    HS_TRY(run_verify(c, L, cnt, mode, d_bitmap + lo / 32, V.run, indexed, nullptr, lane, j == 0 ? 2 : 0));
+    HS_CUDA(c, cudaEventRecord(c->ev_dig[j], c->stream_dig));
   }
-  for (hs_ctx::verify_lane &V : c->lanes) {
-    HS_CUDA(c, cudaEventRecord(V.ev_done, V.run));
-    HS_CUDA(c, cudaStreamWaitEvent(stream, V.ev_done, 0));
+  in_layout L{d_sig, 64, d_pk, 32, d_vidx, d_digests, 32, nullptr, nullptr, 32, 0};
+  main_out O{(fe *)V.xyz.p, (uint8_t *)V.meta.p, 0};
+  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
+  if (!indexed) {
+    key_table T{c->d_slots, c->slot_mask, c->d_pks, (uint32_t)c->n_keys};
+    HS_CUDA(c, cudaMemsetAsync(V.d_miss_count, 0, 4, stream));
+    k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)V.vidx.p, (uint32_t *)V.miss.p, V.d_miss_count);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+    L.vidx = (const uint32_t *)V.vidx.p;
+    O.side_pass = 1;
+    HS_TRY(learn_collect(c, V, L, n, true, stream));
+    // generic pass over the compacted miss list: needs the lookup and EVERY digest; runs beside the main kernels
+    HS_CUDA(c, cudaEventRecord(V.ev_side[0], stream));
+    HS_CUDA(c, cudaStreamWaitEvent(V.side, V.ev_side[0], 0));
+    HS_CUDA(c, cudaStreamWaitEvent(V.side, c->ev_dig[n_chunks - 1], 0));
+    unsigned grid = blocks_for(n, 32);
+    if (grid > 148u * 8u) grid = 148u * 8u;
+    k_verify_main<false><<<grid, 32, 0, V.side>>>(L, 0, V.d_miss_count, (const uint32_t *)V.miss.p, c->d_btable, C, O, c->cp);
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+    HS_CUDA(c, cudaEventRecord(V.ev_side[1], V.side));
   }
+  for (int j = 0; j < n_chunks; j++) {
+    const size_t lo = lo_of[j], cnt = lo_of[j + 1] - lo;
+    HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_dig[j], 0));
+    in_layout Lj = L;
+    Lj.sig = L.sig + lo * 64;
+    Lj.vidx = L.vidx + lo;
+    Lj.msg = L.msg + lo * 32;
+    if (Lj.pk) Lj.pk = L.pk + lo * 32;
+    main_out Oj{O.xyz + lo * 3, O.meta + lo, O.side_pass};
+    if (c->profile_main && j == n_chunks - 1) HS_CUDA(c, cudaEventRecord(c->ev_prof[0], stream));
+    k_verify_main<true><<<blocks_for(cnt), HS_THREADS, 0, stream>>>(Lj, cnt, nullptr, nullptr, c->d_btable, C, Oj, c->cp);
+    if (c->profile_main && j == n_chunks - 1) HS_CUDA(c, cudaEventRecord(c->ev_prof[1], stream));
+    c->launches++;
+    HS_CUDA(c, cudaGetLastError());
+  }
+  if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, V.ev_side[1], 0));
+  const int fin_group = n >= (1u << 19) ? 16 : (n >= (1u << 18) ? 8 : 4);
+  const size_t fin_threads = (n + fin_group - 1) / fin_group;
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)V.xyz.p, (const uint8_t *)V.meta.p, mode, d_bitmap, nullptr, peer_route{},
+                                                                     fin_group);
+  c->launches++;
+  HS_CUDA(c, cudaGetLastError());
   return HS_OK;
 }
 int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const void *d_vidx, const void *d_msgs, size_t msg_len, size_t n,
@@ -1548,7 +1603,8 @@ int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const voi
     return fail(c, HS_ERR_ARG, "hs_verify_msgs_dev: bad argument");
   if (n == 0) return HS_OK;
   HS_CUDA(c, cudaSetDevice(c->device));
-  if (n >= HS_PIPE_MIN && c->pipeline_enabled && !c->peer_armed)
+  // (needs registered / learned keys: with none, every record takes the generic kernel and there is nothing to overlap it with)
+  if (n >= HS_PIPE_MIN && c->pipeline_enabled && !c->peer_armed && c->n_keys > 0 && (!d_vidx || c->explicit_committee))
     return verify_msgs_pipelined(c, (const uint8_t *)d_sig, (const uint8_t *)d_pk, (const uint32_t *)d_vidx, (const uint8_t *)d_msgs, msg_len, n, mode,
                                  (uint8_t *)d_digests, (uint32_t *)d_bitmap, (cudaStream_t)stream);
   // Digest(msg_i) in its own kernel: fusing it into k_verify_main was measured SLOWER on B200 (4.53 vs 4.13 ms per 2^20: the
