@@ -748,19 +748,8 @@ struct dev_buf {
 };
 struct hs_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr, stream2 = nullptr;
-  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  // A verify pass needs scratch (projective results, per-record meta, resolved key indices, the miss list) and a side stream for
-  // the generic pass over unregistered keys.  Two lanes let two passes be in flight at once (hs_verify_msgs_dev pipelines chunks).
-  struct verify_lane {
-    dev_buf xyz, meta, vidx, miss;
-    uint32_t *d_miss_count = nullptr;
-    cudaStream_t side = nullptr;              // high priority: the generic pass over the compacted miss list
-    cudaStream_t run = nullptr;               // lane's own compute stream (pipelined mode)
-    cudaEvent_t ev_side[2] = {nullptr, nullptr}, ev_done = nullptr;
-  } lanes[2];
-  cudaStream_t stream_dig = nullptr;          // high priority: Digest kernels of the chunks ahead (pipelined mode)
-  cudaEvent_t ev_in = nullptr, ev_dig[16] = {};
+  cudaStream_t stream = nullptr, stream2 = nullptr, stream_side = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_side[2] = {nullptr, nullptr};
   ge_niels *d_btable = nullptr;
   comb_params cp{};
   size_t a_table_entries = 0;
@@ -773,7 +762,8 @@ struct hs_ctx {
   uint32_t *d_slots = nullptr;
   uint32_t slot_mask = 0;
   // grow-only device scratch
-  dev_buf in[2], digest[2], out;
+  dev_buf in[2], digest[2], xyz, meta, vidx, miss, out;
+  uint32_t *d_miss_count = nullptr;
   uint32_t *h_miss_count = nullptr;  // pinned
   // key cache: tables for keys that were never registered but keep showing up (learned between calls)
   bool explicit_committee = false;   // hs_committee_register was called with keys: the set is fixed, nothing is learned
@@ -807,7 +797,6 @@ struct hs_ctx {
   uint32_t *d_small_counter = nullptr;
   uint32_t small_seq = 0;
   bool small_enabled = true;
-  bool pipeline_enabled = true;      // env HS_PIPELINE=0: run Digest and verify of a large hs_verify_msgs_dev call back to back (r1 behaviour)
   // optional timing of the dominant kernel alone (bench.py's roofline): events around k_verify_main<committee>
   bool profile_main = false;
   cudaEvent_t ev_prof[2] = {nullptr, nullptr};
@@ -983,7 +972,7 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   return HS_OK;
 }
 // After the lookup of a pass: park the unknown keys for learn_process().
-static int learn_collect(hs_ctx *c, hs_ctx::verify_lane &V, const in_layout &L, size_t n, bool have_lookup, cudaStream_t stream) {
+static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_lookup, cudaStream_t stream) {
   if (!c->cache_enabled || c->explicit_committee || c->learn_pending || !L.pk) return HS_OK;
   if (!c->d_learn_keys) {
     HS_CUDA(c, cudaMalloc(&c->d_learn_keys, (size_t)HS_LEARN_MAX * 32));
@@ -996,13 +985,13 @@ static int learn_collect(hs_ctx *c, hs_ctx::verify_lane &V, const in_layout &L, 
   c->learn_records = n;
   if (c->cache_full) {  // only watch the miss rate
     if (!have_lookup) return HS_OK;
-    HS_CUDA(c, cudaMemcpyAsync(c->h_miss_total, V.d_miss_count, 4, cudaMemcpyDeviceToHost, stream));
+    HS_CUDA(c, cudaMemcpyAsync(c->h_miss_total, c->d_miss_count, 4, cudaMemcpyDeviceToHost, stream));
     HS_CUDA(c, cudaEventRecord(c->ev_learn, stream));
     c->learn_pending = true;
     return HS_OK;
   }
-  k_gather_keys<<<blocks_for(HS_LEARN_MAX, 256), 256, 0, stream>>>(L, n, have_lookup ? (const uint32_t *)V.miss.p : nullptr,
-                                                                     have_lookup ? V.d_miss_count : nullptr, HS_LEARN_MAX, c->d_learn_keys, c->d_learn_n);
+  k_gather_keys<<<blocks_for(HS_LEARN_MAX, 256), 256, 0, stream>>>(L, n, have_lookup ? (const uint32_t *)c->miss.p : nullptr,
+                                                                     have_lookup ? c->d_miss_count : nullptr, HS_LEARN_MAX, c->d_learn_keys, c->d_learn_n);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   HS_CUDA(c, cudaMemcpyAsync(c->h_learn_n, c->d_learn_n, 4, cudaMemcpyDeviceToHost, stream));
@@ -1015,8 +1004,7 @@ static int learn_collect(hs_ctx *c, hs_ctx::verify_lane &V, const in_layout &L, 
 // Runs lookup (optional) -> main (committee and/or generic) -> finish on `stream` for a device-resident layout.
 // use_lookup: L.pk is valid and a committee is registered -> resolve indices on the device.
 static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t *d_bitmap, cudaStream_t stream, bool indexed,
-                      uint8_t *d_flags_out = nullptr, int lane = 0, int learn = 3 /* bit 0: build pending tables, bit 1: collect unknown keys */) {
-  hs_ctx::verify_lane &V = c->lanes[lane];
+                      uint8_t *d_flags_out = nullptr) {
   if (n == 0) {
     if (c->peer_armed) {  // an empty shard still owes its peers the epoch flag
       c->peer_armed = false;
@@ -1027,45 +1015,45 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     return HS_OK;
   }
   if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
-  if (!indexed && (learn & 1)) HS_TRY(learn_process(c, stream));
-  HS_TRY(ensure(c, V.xyz, n * 3 * sizeof(fe)));
-  HS_TRY(ensure(c, V.meta, n));
-  main_out O{(fe *)V.xyz.p, (uint8_t *)V.meta.p, 0};
+  if (!indexed) HS_TRY(learn_process(c, stream));
+  HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, c->meta, n));
+  main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, 0};
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
   if (!committee && !L.pk) return fail(c, HS_ERR_ARG, "verify without keys");
   if (committee) {
     if (!indexed) {
-      HS_TRY(ensure(c, V.vidx, n * 4));
-      HS_TRY(ensure(c, V.miss, n * 4));
+      HS_TRY(ensure(c, c->vidx, n * 4));
+      HS_TRY(ensure(c, c->miss, n * 4));
       key_table T{c->d_slots, c->slot_mask, c->d_pks, (uint32_t)c->n_keys};
-      HS_CUDA(c, cudaMemsetAsync(V.d_miss_count, 0, 4, stream));
-      k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)V.vidx.p, (uint32_t *)V.miss.p, V.d_miss_count);
+      HS_CUDA(c, cudaMemsetAsync(c->d_miss_count, 0, 4, stream));
+      k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)c->vidx.p, (uint32_t *)c->miss.p, c->d_miss_count);
       c->launches++;
       HS_CUDA(c, cudaGetLastError());
-      L.vidx = (const uint32_t *)V.vidx.p;
+      L.vidx = (const uint32_t *)c->vidx.p;
       O.side_pass = 1;
-      if (learn & 2) HS_TRY(learn_collect(c, V, L, n, true, stream));
+      HS_TRY(learn_collect(c, L, n, true, stream));
       // Records whose key is not registered take the generic path over the compacted list.  One generic verify has a
       // ~0.8 ms single-warp latency, so the pass runs on the high-priority side stream CONCURRENTLY with the committee
       // pass (disjoint outputs); its length stays on the device (no host round trip).
-      HS_CUDA(c, cudaEventRecord(V.ev_side[0], stream));
-      HS_CUDA(c, cudaStreamWaitEvent(V.side, V.ev_side[0], 0));
+      HS_CUDA(c, cudaEventRecord(c->ev_side[0], stream));
+      HS_CUDA(c, cudaStreamWaitEvent(c->stream_side, c->ev_side[0], 0));
       unsigned grid = blocks_for(n, 32);
       if (grid > 148u * 8u) grid = 148u * 8u;
-      k_verify_main<false><<<grid, 32, 0, V.side>>>(L, 0, V.d_miss_count, (const uint32_t *)V.miss.p, c->d_btable, C, O, c->cp);
+      k_verify_main<false><<<grid, 32, 0, c->stream_side>>>(L, 0, c->d_miss_count, (const uint32_t *)c->miss.p, c->d_btable, C, O, c->cp);
       c->launches++;
       HS_CUDA(c, cudaGetLastError());
-      HS_CUDA(c, cudaEventRecord(V.ev_side[1], V.side));
+      HS_CUDA(c, cudaEventRecord(c->ev_side[1], c->stream_side));
     }
     if (c->profile_main) HS_CUDA(c, cudaEventRecord(c->ev_prof[0], stream));
     k_verify_main<true><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     if (c->profile_main) HS_CUDA(c, cudaEventRecord(c->ev_prof[1], stream));
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
-    if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, V.ev_side[1], 0));
+    if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_side[1], 0));
   } else {
-    if (learn & 2) HS_TRY(learn_collect(c, V, L, n, false, stream));
+    HS_TRY(learn_collect(c, L, n, false, stream));
     k_verify_main<false><<<blocks_for(n), HS_THREADS, 0, stream>>>(L, n, nullptr, nullptr, c->d_btable, C, O, c->cp);
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
@@ -1077,7 +1065,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     P = c->peers;
     c->peer_armed = false;
   }
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)V.xyz.p, (const uint8_t *)V.meta.p, mode, d_bitmap, d_flags_out, P, fin_group);
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, d_flags_out, P, fin_group);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;
@@ -1182,21 +1170,17 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
-  int prio_lo = 0, prio_hi = 0;
-  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream_dig, cudaStreamNonBlocking, prio_hi);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
-  for (int i = 0; i < 16 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_dig[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&c->stream_side, cudaStreamNonBlocking, hi);
+  }
   for (int i = 0; i < 2 && e == cudaSuccess; i++) {
     e = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
-    hs_ctx::verify_lane &V = c->lanes[i];
-    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&V.side, cudaStreamNonBlocking, prio_hi);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&V.run, cudaStreamNonBlocking);
-    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&V.ev_side[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&V.ev_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc(&V.d_miss_count, 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_side[i], cudaEventDisableTiming);
   }
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
   if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_in, HS_SMALL_MAX * sizeof(small_rec), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_out, 256, cudaHostAllocMapped);
@@ -1205,7 +1189,6 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   if (e == cudaSuccess) e = cudaMemset(c->d_small_counter, 0, 4);
   if (e == cudaSuccess) *c->h_small_done = 0;
   c->small_enabled = !(getenv("HS_SMALL_PATH") && getenv("HS_SMALL_PATH")[0] == '0');
-  c->pipeline_enabled = !(getenv("HS_PIPELINE") && getenv("HS_PIPELINE")[0] == '0');
   set_window(c->cp, false, wb);
   set_window(c->cp, true, 12);
   c->wa_forced = (int)((flags >> 8) & 0xffu);
@@ -1234,24 +1217,13 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_key_flags);
   cudaFree(c->d_atables);
   cudaFree(c->d_slots);
-  for (hs_ctx::verify_lane &V : c->lanes) {
-    cudaFree(V.d_miss_count);
-    for (dev_buf *b : {&V.xyz, &V.meta, &V.vidx, &V.miss}) cudaFree(b->p);
-    for (cudaEvent_t ev : {V.ev_side[0], V.ev_side[1], V.ev_done})
-      if (ev) cudaEventDestroy(ev);
-    if (V.side) cudaStreamDestroy(V.side);
-    if (V.run) cudaStreamDestroy(V.run);
-  }
-  if (c->ev_in) cudaEventDestroy(c->ev_in);
-  for (cudaEvent_t ev : c->ev_dig)
-    if (ev) cudaEventDestroy(ev);
-  if (c->stream_dig) cudaStreamDestroy(c->stream_dig);
+  cudaFree(c->d_miss_count);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
   if (c->h_small_in) cudaFreeHost(c->h_small_in);
   if (c->h_small_out) cudaFreeHost(c->h_small_out);
   if (c->h_small_done) cudaFreeHost(c->h_small_done);
   cudaFree(c->d_small_counter);
-  for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->out}) cudaFree(b->p);
+  for (dev_buf *b : {&c->in[0], &c->in[1], &c->digest[0], &c->digest[1], &c->xyz, &c->meta, &c->vidx, &c->miss, &c->out}) cudaFree(b->p);
   cudaFree(c->d_learn_keys);
   cudaFree(c->d_learn_n);
   if (c->h_learn_keys) cudaFreeHost(c->h_learn_keys);
@@ -1266,7 +1238,9 @@ void hs_ctx_destroy(hs_ctx *c) {
   for (int i = 0; i < 2; i++) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    if (c->ev_side[i]) cudaEventDestroy(c->ev_side[i]);
   }
+  if (c->stream_side) cudaStreamDestroy(c->stream_side);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
@@ -1512,101 +1486,12 @@ int hs_digest32_fixed_dev(hs_ctx *c, const void *d_msgs, size_t msg_len, size_t 
   HS_CUDA(c, cudaSetDevice(c->device));
   return launch_digest_fixed(c, (const uint8_t *)d_msgs, msg_len, n, (uint32_t *)d_out, (cudaStream_t)stream);
 }
-// Large resident batches: the Digest kernel (ALU pipe: funnel shifts / LOP3 / adds, 94 % busy) and the verify main kernel
-// (FMA-heavy pipe: wide multiplies, 83 % busy) bind DIFFERENT issue pipes, so they are made to share the SMs instead of running back
-// to back: the messages are hashed in growing chunks on a high-priority stream while the main kernel of every chunk whose digests
-// are ready runs on the caller's stream.  One key lookup, one generic side pass (records with unregistered keys) and one finish
-// kernel serve the whole batch, exactly as in the single-pass form.
-#define HS_PIPE_MIN ((size_t)1 << 18)
-#define HS_PIPE_MAX_CHUNKS 16
-static int verify_msgs_pipelined(hs_ctx *c, const uint8_t *d_sig, const uint8_t *d_pk, const uint32_t *d_vidx, const uint8_t *d_msgs, size_t msg_len,
-                                 size_t n, uint32_t mode, uint8_t *d_digests, uint32_t *d_bitmap, cudaStream_t stream) {
-  const bool indexed = d_vidx != nullptr;
-  hs_ctx::verify_lane &V = c->lanes[0];
-  if (!indexed) HS_TRY(learn_process(c, stream));
-  HS_TRY(ensure(c, V.xyz, n * 3 * sizeof(fe)));
-  HS_TRY(ensure(c, V.meta, n));
-  if (!indexed) {
-    HS_TRY(ensure(c, V.vidx, n * 4));
-    HS_TRY(ensure(c, V.miss, n * 4));
-  }
-  // chunk sizes: 2^16, 2^16, 2^17, 2^18, 2^18, ... — a short first chunk starts the verify kernels early, long later chunks keep whole waves
-  size_t lo_of[HS_PIPE_MAX_CHUNKS + 1];
-  int n_chunks = 0;
-  {
-    size_t lo = 0, sz = (size_t)1 << 16;
-    while (lo < n && n_chunks < HS_PIPE_MAX_CHUNKS - 1) {
-      lo_of[n_chunks++] = lo;
-      lo += sz;
-      if (n_chunks >= 2 && sz < ((size_t)1 << 18)) sz <<= 1;
-    }
-    if (lo < n) lo_of[n_chunks++] = lo;  // whatever is left goes into the last chunk
-    lo_of[n_chunks] = n;
-  }
-  HS_CUDA(c, cudaEventRecord(c->ev_in, stream));
-  HS_CUDA(c, cudaStreamWaitEvent(c->stream_dig, c->ev_in, 0));
-  for (int j = 0; j < n_chunks; j++) {
-    const size_t lo = lo_of[j], cnt = lo_of[j + 1] - lo;
-    HS_TRY(launch_digest_fixed(c, d_msgs + lo * msg_len, msg_len, cnt, (uint32_t *)(d_digests + lo * 32), c->stream_dig));
-    HS_CUDA(c, cudaEventRecord(c->ev_dig[j], c->stream_dig));
-  }
-  in_layout L{d_sig, 64, d_pk, 32, d_vidx, d_digests, 32, nullptr, nullptr, 32, 0};
-  main_out O{(fe *)V.xyz.p, (uint8_t *)V.meta.p, 0};
-  committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
-  if (!indexed) {
-    key_table T{c->d_slots, c->slot_mask, c->d_pks, (uint32_t)c->n_keys};
-    HS_CUDA(c, cudaMemsetAsync(V.d_miss_count, 0, 4, stream));
-    k_key_lookup<<<blocks_for(n, 256), 256, 0, stream>>>(L, n, T, (uint32_t *)V.vidx.p, (uint32_t *)V.miss.p, V.d_miss_count);
-    c->launches++;
-    HS_CUDA(c, cudaGetLastError());
-    L.vidx = (const uint32_t *)V.vidx.p;
-    O.side_pass = 1;
-    HS_TRY(learn_collect(c, V, L, n, true, stream));
-    // generic pass over the compacted miss list: needs the lookup and EVERY digest; runs beside the main kernels
-    HS_CUDA(c, cudaEventRecord(V.ev_side[0], stream));
-    HS_CUDA(c, cudaStreamWaitEvent(V.side, V.ev_side[0], 0));
-    HS_CUDA(c, cudaStreamWaitEvent(V.side, c->ev_dig[n_chunks - 1], 0));
-    unsigned grid = blocks_for(n, 32);
-    if (grid > 148u * 8u) grid = 148u * 8u;
-    k_verify_main<false><<<grid, 32, 0, V.side>>>(L, 0, V.d_miss_count, (const uint32_t *)V.miss.p, c->d_btable, C, O, c->cp);
-    c->launches++;
-    HS_CUDA(c, cudaGetLastError());
-    HS_CUDA(c, cudaEventRecord(V.ev_side[1], V.side));
-  }
-  for (int j = 0; j < n_chunks; j++) {
-    const size_t lo = lo_of[j], cnt = lo_of[j + 1] - lo;
-    HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_dig[j], 0));
-    in_layout Lj = L;
-    Lj.sig = L.sig + lo * 64;
-    Lj.vidx = L.vidx + lo;
-    Lj.msg = L.msg + lo * 32;
-    if (Lj.pk) Lj.pk = L.pk + lo * 32;
-    main_out Oj{O.xyz + lo * 3, O.meta + lo, O.side_pass};
-    if (c->profile_main && j == n_chunks - 1) HS_CUDA(c, cudaEventRecord(c->ev_prof[0], stream));
-    k_verify_main<true><<<blocks_for(cnt), HS_THREADS, 0, stream>>>(Lj, cnt, nullptr, nullptr, c->d_btable, C, Oj, c->cp);
-    if (c->profile_main && j == n_chunks - 1) HS_CUDA(c, cudaEventRecord(c->ev_prof[1], stream));
-    c->launches++;
-    HS_CUDA(c, cudaGetLastError());
-  }
-  if (!indexed) HS_CUDA(c, cudaStreamWaitEvent(stream, V.ev_side[1], 0));
-  const int fin_group = n >= (1u << 19) ? 16 : (n >= (1u << 18) ? 8 : 4);
-  const size_t fin_threads = (n + fin_group - 1) / fin_group;
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)V.xyz.p, (const uint8_t *)V.meta.p, mode, d_bitmap, nullptr, peer_route{},
-                                                                     fin_group);
-  c->launches++;
-  HS_CUDA(c, cudaGetLastError());
-  return HS_OK;
-}
 int hs_verify_msgs_dev(hs_ctx *c, const void *d_sig, const void *d_pk, const void *d_vidx, const void *d_msgs, size_t msg_len, size_t n,
                        uint32_t mode, void *d_digests, void *d_bitmap, void *stream) {
   if (!c || mode > 1 || (n && (!d_sig || (!d_pk && !d_vidx) || !d_msgs || !d_digests || !d_bitmap)))
     return fail(c, HS_ERR_ARG, "hs_verify_msgs_dev: bad argument");
   if (n == 0) return HS_OK;
   HS_CUDA(c, cudaSetDevice(c->device));
-  // (needs registered / learned keys: with none, every record takes the generic kernel and there is nothing to overlap it with)
-  if (n >= HS_PIPE_MIN && c->pipeline_enabled && !c->peer_armed && c->n_keys > 0 && (!d_vidx || c->explicit_committee))
-    return verify_msgs_pipelined(c, (const uint8_t *)d_sig, (const uint8_t *)d_pk, (const uint32_t *)d_vidx, (const uint8_t *)d_msgs, msg_len, n, mode,
-                                 (uint8_t *)d_digests, (uint32_t *)d_bitmap, (cudaStream_t)stream);
   // Digest(msg_i) in its own kernel: fusing it into k_verify_main was measured SLOWER on B200 (4.53 vs 4.13 ms per 2^20: the
   // SHA phase then runs at the curve kernel's 128-register occupancy and the two phases do not overlap across pipes in practice).
   HS_TRY(launch_digest_fixed(c, (const uint8_t *)d_msgs, msg_len, n, (uint32_t *)d_digests, (cudaStream_t)stream));
@@ -2099,11 +1984,11 @@ int hs_verify_msgs(hs_ctx *c, const uint8_t *sig, const uint8_t *pk, const uint3
     HS_TRY(ensure(c, c->in[b], chunk_cap * per_rec + 64));
     HS_TRY(ensure(c, c->digest[b], chunk_cap * 32));
   }
-  HS_TRY(ensure(c, c->lanes[0].xyz, chunk_cap * 3 * sizeof(fe)));
-  HS_TRY(ensure(c, c->lanes[0].meta, chunk_cap));
+  HS_TRY(ensure(c, c->xyz, chunk_cap * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, c->meta, chunk_cap));
   if (!vidx && c->n_keys) {
-    HS_TRY(ensure(c, c->lanes[0].vidx, chunk_cap * 4));
-    HS_TRY(ensure(c, c->lanes[0].miss, chunk_cap * 4));
+    HS_TRY(ensure(c, c->vidx, chunk_cap * 4));
+    HS_TRY(ensure(c, c->miss, chunk_cap * 4));
   }
   // (A short "ramp" first chunk was tried and measured slower — 7.1e7 vs 7.6e7 verifies/s: every extra chunk costs one more
   // generic-pass latency when the batch contains unknown keys.)
