@@ -255,6 +255,11 @@ def qc_leg(eng, torch, dist, dev, rank, world, committee, qcs, votes_per_qc, ste
             if rank == 0:
                 print("peer all-gather unavailable, using ncclAllGather: %s" % ex, file=sys.stderr)
 
+    # deferred-results mode: the finish kernel (+ peer exchange) and the per-QC AND of pass i run on the engine's tail stream beside the
+    # main kernel of pass i+1; hs_results_wait() closes the timed region.  (Not with ncclAllGather: the collective needs the bitmap on torch's stream.)
+    deferred = world == 1 or pag is not None
+    eng.set_deferred(deferred)
+
     def step():
         eng.digest32_fixed_dev(d_pre, 40, d_dig, qcs)                                       # QC::digest for every certificate
         if pag is not None:
@@ -272,6 +277,8 @@ def qc_leg(eng, torch, dist, dev, rank, world, committee, qcs, votes_per_qc, ste
 
     for _ in range(max(3, warmup)):
         full = step()
+    if deferred:
+        eng.results_wait()
     torch.cuda.synchronize()
     bits = np.unpackbits(full.cpu().numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
     assert (bits == ~inp["corrupted"]).all(), "vote verdicts differ from the expected pattern"
@@ -287,6 +294,8 @@ def qc_leg(eng, torch, dist, dev, rank, world, committee, qcs, votes_per_qc, ste
     e0.record()
     for _ in range(steps):
         step()
+    if deferred:
+        eng.results_wait()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -296,7 +305,8 @@ def qc_leg(eng, torch, dist, dev, rank, world, committee, qcs, votes_per_qc, ste
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     wa, wb = eng.window_bits
-    return {"votes": n, "committee": committee, "qcs": qcs, "votes_per_qc": votes_per_qc, "ms_per_step": ms / steps, "votes_per_s": n * steps / (ms * 1e-3),
+    eng.set_deferred(False)
+    return {"votes": n, "deferred_results": deferred, "committee": committee, "qcs": qcs, "votes_per_qc": votes_per_qc, "ms_per_step": ms / steps, "votes_per_s": n * steps / (ms * 1e-3),
             "gpu_launches_per_step": int(eng.kernel_launches - l0) // steps, "window_bits": {"key": wa, "base": wb}, "votes_per_rank": per,
             "collective": "none (1 rank)" if world == 1 else ("fused peer-store all-gather inside the finish kernel (NVLink P2P)" if pag is not None else "ncclAllGather"),
             "scaling": "strong"}

@@ -44,6 +44,8 @@ SIGNATURES = {
     "hs_sign_digests": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "hs_keygen_batch_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "hs_sign_digests_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "hs_set_deferred": (c_int, [c_void_p, c_int]),
+    "hs_results_wait": (c_int, [c_void_p, c_void_p]),
     "hs_peer_setup": (c_int, [c_void_p, c_int, c_int, c_size_t, c_void_p]),
     "hs_peer_open": (c_int, [c_void_p, c_int, c_void_p]),
     "hs_peer_next": (c_int, [c_void_p, c_size_t, c_u32]),

@@ -797,6 +797,13 @@ struct hs_ctx {
   uint32_t *d_small_counter = nullptr;
   uint32_t small_seq = 0;
   bool small_enabled = true;
+  // deferred-results mode (hs_set_deferred): the latency-bound tail of a `_dev` verify pass (finish kernel, peer exchange, per-QC AND)
+  // runs on an internal stream so that it overlaps the main kernel of the NEXT pass; two scratch sets alternate
+  bool deferred = false;
+  cudaStream_t stream_tail = nullptr;
+  cudaEvent_t ev_main_done = nullptr, ev_tail[2] = {nullptr, nullptr}, ev_results = nullptr;
+  dev_buf xyz2, meta2;
+  int flip = 0;
   // optional timing of the dominant kernel alone (bench.py's roofline): events around k_verify_main<committee>
   bool profile_main = false;
   cudaEvent_t ev_prof[2] = {nullptr, nullptr};
@@ -1016,9 +1023,15 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   }
   if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (!indexed) HS_TRY(learn_process(c, stream));
-  HS_TRY(ensure(c, c->xyz, n * 3 * sizeof(fe)));
-  HS_TRY(ensure(c, c->meta, n));
-  main_out O{(fe *)c->xyz.p, (uint8_t *)c->meta.p, 0};
+  dev_buf &XYZ = (c->deferred && c->flip) ? c->xyz2 : c->xyz, &META = (c->deferred && c->flip) ? c->meta2 : c->meta;
+  const int set = c->deferred ? c->flip : 0;
+  if (c->deferred) {
+    c->flip ^= 1;
+    HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_tail[set], 0));  // the finish kernel that last read this scratch set is done
+  }
+  HS_TRY(ensure(c, XYZ, n * 3 * sizeof(fe)));
+  HS_TRY(ensure(c, META, n));
+  main_out O{(fe *)XYZ.p, (uint8_t *)META.p, 0};
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
   const bool committee = c->n_keys > 0 && (indexed || L.pk);
   if (!committee && !L.pk) return fail(c, HS_ERR_ARG, "verify without keys");
@@ -1065,9 +1078,16 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     P = c->peers;
     c->peer_armed = false;
   }
-  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, stream>>>(L, n, (const fe *)c->xyz.p, (const uint8_t *)c->meta.p, mode, d_bitmap, d_flags_out, P, fin_group);
+  cudaStream_t fin_stream = stream;
+  if (c->deferred) {  // tail on the internal stream: the caller's stream is free for the next pass's digest / main kernels
+    HS_CUDA(c, cudaEventRecord(c->ev_main_done, stream));
+    HS_CUDA(c, cudaStreamWaitEvent(c->stream_tail, c->ev_main_done, 0));
+    fin_stream = c->stream_tail;
+  }
+  k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, fin_stream>>>(L, n, (const fe *)XYZ.p, (const uint8_t *)META.p, mode, d_bitmap, d_flags_out, P, fin_group);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
+  if (c->deferred) HS_CUDA(c, cudaEventRecord(c->ev_tail[set], c->stream_tail));
   return HS_OK;
 }
 
@@ -1182,6 +1202,10 @@ int hs_ctx_create(hs_ctx **out, int device, uint32_t flags) {
   }
   if (e == cudaSuccess) e = cudaMalloc(&c->d_miss_count, 4);
   if (e == cudaSuccess) e = cudaMallocHost(&c->h_miss_count, 4);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_tail, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_main_done, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_results, cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_tail[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_in, HS_SMALL_MAX * sizeof(small_rec), cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_out, 256, cudaHostAllocMapped);
   if (e == cudaSuccess) e = cudaHostAlloc(&c->h_small_done, 64, cudaHostAllocMapped);
@@ -1219,6 +1243,11 @@ void hs_ctx_destroy(hs_ctx *c) {
   cudaFree(c->d_slots);
   cudaFree(c->d_miss_count);
   if (c->h_miss_count) cudaFreeHost(c->h_miss_count);
+  cudaFree(c->xyz2.p);
+  cudaFree(c->meta2.p);
+  for (cudaEvent_t ev : {c->ev_main_done, c->ev_tail[0], c->ev_tail[1], c->ev_results})
+    if (ev) cudaEventDestroy(ev);
+  if (c->stream_tail) cudaStreamDestroy(c->stream_tail);
   if (c->h_small_in) cudaFreeHost(c->h_small_in);
   if (c->h_small_out) cudaFreeHost(c->h_small_out);
   if (c->h_small_done) cudaFreeHost(c->h_small_done);
@@ -1255,6 +1284,26 @@ void hs_window_bits(const hs_ctx *c, int *key_bits, int *base_bits) {
 uint64_t hs_kernel_launches(const hs_ctx *c) { return c ? c->launches.load() : 0; }
 /* Measurement hook: with profiling on, CUDA events bracket the k_verify_main<committee> launch of every verify pass on the stream the
  * pass runs on; hs_profile_main_ms() waits for the last pass and returns that kernel's duration in ms (< 0: nothing recorded). */
+/* Deferred-results mode for streams of `_dev` verify passes: the tail of a pass (finish kernel + peer exchange, hs_qc_and_dev) runs on an
+ * internal stream and overlaps the NEXT pass's kernels; verdict bitmaps are complete only after hs_results_wait(ctx, stream) (which makes
+ * `stream` wait for every tail enqueued so far).  Inputs of a pass (signatures) must stay valid until then.  Host-pointer entry points are
+ * unaffected: switch the mode only while no pass is in flight. */
+int hs_set_deferred(hs_ctx *c, int on) {
+  if (!c) return HS_ERR_ARG;
+  std::lock_guard<std::mutex> g(c->mu);
+  HS_CUDA(c, cudaSetDevice(c->device));
+  HS_CUDA(c, cudaDeviceSynchronize());
+  c->deferred = on != 0;
+  c->flip = 0;
+  return HS_OK;
+}
+int hs_results_wait(hs_ctx *c, void *stream) {
+  if (!c) return HS_ERR_ARG;
+  HS_CUDA(c, cudaSetDevice(c->device));
+  HS_CUDA(c, cudaEventRecord(c->ev_results, c->stream_tail));
+  HS_CUDA(c, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_results, 0));
+  return HS_OK;
+}
 int hs_profile_enable(hs_ctx *c, int on) {
   if (!c) return HS_ERR_ARG;
   std::lock_guard<std::mutex> g(c->mu);
@@ -1555,10 +1604,10 @@ int hs_verify_qc_votes_dev(hs_ctx *c, const void *d_qc_digests, const void *d_pk
 int hs_qc_and_dev(hs_ctx *c, const void *d_vote_bitmap, const void *d_qc_idx, size_t n_votes, size_t n_qc, void *d_qc_bitmap, void *stream) {
   if (!c || !d_qc_bitmap || (n_votes && (!d_vote_bitmap || !d_qc_idx))) return fail(c, HS_ERR_ARG, "hs_qc_and_dev: bad argument");
   HS_CUDA(c, cudaSetDevice(c->device));
-  if (n_qc) k_bitmap_ones<<<blocks_for((n_qc + 31) / 32, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t *)d_qc_bitmap, n_qc);
+  cudaStream_t st = c->deferred ? c->stream_tail : (cudaStream_t)stream;  // deferred mode: ordered after the finish kernel on the tail stream
+  if (n_qc) k_bitmap_ones<<<blocks_for((n_qc + 31) / 32, 256), 256, 0, st>>>((uint32_t *)d_qc_bitmap, n_qc);
   if (n_votes)
-    k_qc_and<<<blocks_for(n_votes, 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t *)d_vote_bitmap, (const uint32_t *)d_qc_idx, n_votes, n_qc,
-                                                                        (uint32_t *)d_qc_bitmap);
+    k_qc_and<<<blocks_for(n_votes, 256), 256, 0, st>>>((const uint32_t *)d_vote_bitmap, (const uint32_t *)d_qc_idx, n_votes, n_qc, (uint32_t *)d_qc_bitmap);
   c->launches += (n_qc ? 1 : 0) + (n_votes ? 1 : 0);
   HS_CUDA(c, cudaGetLastError());
   return HS_OK;

@@ -280,6 +280,13 @@ class Engine:
         self._check(self.lib.hs_sign_digests_dev(self.h, d_seeds.data_ptr(), d_pks.data_ptr(), n_keys, None if d_key_idx is None else d_key_idx.data_ptr(),
                                                  d_digests.data_ptr(), n, d_sig.data_ptr(), self._stream()), "hs_sign_digests_dev")
 
+    def set_deferred(self, on):
+        """Deferred-results mode for streams of `_dev` passes (hs_set_deferred): call results_wait() before reading bitmaps."""
+        self._check(self.lib.hs_set_deferred(self.h, 1 if on else 0), "hs_set_deferred")
+
+    def results_wait(self):
+        self._check(self.lib.hs_results_wait(self.h, self._stream()), "hs_results_wait")
+
     def digest32_fixed_dev(self, d_msgs, msg_len, d_out, n):
         self._check(self.lib.hs_digest32_fixed_dev(self.h, d_msgs.data_ptr(), msg_len, n, d_out.data_ptr(), self._stream()), "hs_digest32_fixed_dev")
 

@@ -219,6 +219,14 @@ int hs_keygen_batch_dev(hs_ctx *ctx, const void *d_seeds, size_t n, void *d_pks,
 int hs_sign_digests_dev(hs_ctx *ctx, const void *d_seeds, const void *d_pks, size_t n_keys, const void *d_key_idx_or_null, const void *d_digests,
                         size_t n, void *d_sig, void *stream);
 
+/* Deferred-results mode for STREAMS of `_dev` verify passes (e.g. one pass per QC burst): the latency-bound tail of a pass — finish
+ * kernel incl. the peer exchange, hs_qc_and_dev — runs on an internal stream and overlaps the main kernel of the next pass (a serial
+ * field inversion per block makes the tail ~80 us however small the pass).  Bitmaps are complete only after hs_results_wait(ctx, stream),
+ * which makes `stream` wait for every tail enqueued so far; the signatures of a pass must stay valid until then.  Host-pointer entry points
+ * must not be mixed with deferred passes in flight. */
+int hs_set_deferred(hs_ctx *ctx, int on);
+int hs_results_wait(hs_ctx *ctx, void *stream);
+
 /* ---- multi-GPU: fused all-gather of the accept bitmap (one process per GPU, same node, NVLink) ------------------------
  * Each rank creates a result buffer for the GLOBAL bitmap (total_words) and exports a 64-byte CUDA-IPC handle; the host
  * exchanges handles (e.g. torch.distributed.all_gather_object) and opens every peer's.  hs_peer_next() then arms the next

@@ -666,3 +666,52 @@ def test_gpu_signer_is_byte_identical_to_rfc8032(engine, oracle, golden):
     sig = engine.sign_digests(sd, pk, dg, key_idx=ki)
     assert (sig == oracle.sign_batch(sd, pk, ki, dg.reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)).all()
     assert engine.verify_rec128(np.concatenate([sig, pk[ki], dg], axis=1)).all()
+
+
+def test_deferred_results_mode(oracle):
+    """hs_set_deferred: the finish kernel of pass i runs on the engine's tail stream beside the main kernel of pass i+1 (two scratch
+    sets alternate).  Twelve back-to-back passes with different inputs and sizes, no synchronisation in between; every pass's bitmap
+    and per-QC AND must equal the oracle after hs_results_wait()."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hotstuff_b200 import Engine
+    e = Engine(0, base_window=16)
+    try:
+        dev = torch.device("cuda", 0)
+        rng = np.random.default_rng(77)
+        N, Q = 60, 40
+        seeds = rng.integers(0, 256, (N, 32), dtype=np.uint8)
+        pks = oracle.keygen_batch(seeds)
+        assert e.committee_register(pks).all()
+        passes = []
+        for p in range(12):
+            n = int(rng.integers(500, 9000))
+            pre = rng.integers(0, 256, (Q, 40), dtype=np.uint8)
+            dig = oracle.digest32_batch(pre.reshape(-1), np.arange(Q + 1, dtype=np.uint64) * 40)
+            qi = rng.integers(0, Q, n).astype(np.uint32)
+            vi = rng.integers(0, N, n).astype(np.uint32)
+            sig = oracle.sign_batch(seeds, pks, vi, dig[qi].reshape(-1), np.arange(n + 1, dtype=np.uint64) * 32)
+            bad = rng.choice(n, n // 20, replace=False)
+            sig[bad, rng.integers(0, 64, len(bad))] ^= 0x20
+            want = oracle.verify_rec128(np.concatenate([sig, pks[vi], dig[qi]], axis=1), mode=1)
+            want_qc = np.ones(Q, dtype=bool)
+            np.logical_and.at(want_qc, qi, want)
+            t = dict(n=n, want=want, want_qc=want_qc, d_pre=torch.from_numpy(pre.reshape(-1)).to(dev), d_dig=torch.empty((Q, 32), dtype=torch.uint8, device=dev),
+                     d_sig=torch.from_numpy(sig).to(dev), d_vi=torch.from_numpy(vi.astype(np.int32)).to(dev), d_qi=torch.from_numpy(qi.astype(np.int32)).to(dev),
+                     d_bm=torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev), d_qc=torch.zeros((Q + 31) // 32, dtype=torch.int32, device=dev))
+            passes.append(t)
+        e.set_deferred(True)
+        for t in passes:
+            e.digest32_fixed_dev(t["d_pre"], 40, t["d_dig"], Q)
+            e.verify_qc_votes_dev(t["d_dig"], t["d_sig"], t["d_qi"], t["d_bm"], t["n"], d_vidx=t["d_vi"])
+            e.qc_and_dev(t["d_bm"], t["d_qi"], t["n"], Q, t["d_qc"])
+        e.results_wait()
+        torch.cuda.synchronize()
+        e.set_deferred(False)
+        for k, t in enumerate(passes):
+            bits = np.unpackbits(t["d_bm"].cpu().numpy().view(np.uint8), bitorder="little")[:t["n"]].astype(bool)
+            qcb = np.unpackbits(t["d_qc"].cpu().numpy().view(np.uint8), bitorder="little")[:Q].astype(bool)
+            assert (bits == t["want"]).all() and (qcb == t["want_qc"]).all(), k
+    finally:
+        e.close()
