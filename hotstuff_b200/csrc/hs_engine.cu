@@ -851,6 +851,7 @@ static int ensure(hs_ctx *c, dev_buf &b, size_t need) {
 }
 static inline unsigned blocks_for(size_t n, unsigned per = HS_THREADS) { return (unsigned)((n + per - 1) / per); }
 
+
 static int launch_build(hs_ctx *c, const uint8_t *d_encs, size_t n_points, int negate, int W, int n_windows, ge_niels *tables, uint8_t *flags) {
   size_t threads = n_points * (size_t)n_windows * ((1u << (W - 1)) / HS_BUILD_BLOCK);
   k_build_comb<<<blocks_for(threads), HS_THREADS, 0, c->stream>>>(d_encs, n_points, negate, W, n_windows, tables, flags);
@@ -1071,7 +1072,9 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     c->launches++;
     HS_CUDA(c, cudaGetLastError());
   }
-  const int fin_group = n >= (1u << 19) ? 16 : (n >= (1u << 18) ? 8 : 4);
+  // small batches: small groups, so that enough blocks exist to hide each block's serial inversion; when the tail overlaps the next pass
+  // (deferred mode) latency is hidden anyway and the 16-record group costs the fewest inversions
+  const int fin_group = (c->deferred || n >= (1u << 19)) ? 16 : (n >= (1u << 18) ? 8 : 4);
   const size_t fin_threads = (n + fin_group - 1) / fin_group;
   peer_route P{};
   if (c->peer_armed) {
