@@ -1374,7 +1374,7 @@ static int committee_register_locked(hs_ctx *c, const uint8_t *pks, size_t N, ui
     if (!dup) slots[h] = (uint32_t)i;
   }
   int wa = 8;
-  for (int w : {16, 15, 14, 13, 12, 11, 10, 9, 8}) {
+  for (int w : {17, 16, 15, 14, 13, 12, 11, 10, 9, 8}) {  // 17 bits: 15 windows (94 MB per key: committees up to ~1,200 keys); 18 would still need 15
     if (c->wa_forced && w != c->wa_forced) continue;
     wa = w;
     if (capk * comb_table_entries(w) * sizeof(ge_niels) <= budget) break;

@@ -53,7 +53,7 @@ typedef struct {
 /* ---- lifecycle ------------------------------------------------------------------------------------------------ */
 /* device: CUDA ordinal.  Builds the base-point comb table on the GPU (default window 24 bits = 8.9 GB of HBM).
  * flags: 0 = defaults; bits 0-7 = base-point window width (even, 8..26; 26 = 10 windows in 32 GB, one addition fewer per verify), bits 8-15 = forced per-key window width
- * (8..16; 0 = widest that fits ~62 % of device memory); HS_FLAG_NO_KEY_CACHE disables the key cache (also env HS_KEY_CACHE=0). */
+ * (8..17; 0 = widest that fits ~62 % of device memory); HS_FLAG_NO_KEY_CACHE disables the key cache (also env HS_KEY_CACHE=0). */
 int hs_ctx_create(hs_ctx **out, int device, uint32_t flags);
 void hs_ctx_destroy(hs_ctx *ctx);
 /* Human-readable description of the last failure on this context (never NULL). */
@@ -159,7 +159,7 @@ typedef struct {
 int hs_ingest_consensus_frames(const uint8_t *frames, const uint64_t *off /* n + 1 */, size_t n, hs_frame_info *info /* n */, hs_ingest_out *out);
 
 /* ---- committee mode: keys registered once per epoch (consensus/src/config.rs:28-60 Committee) ------------------- */
-/* Decompresses every key and builds its comb table in HBM (window 16 bits: 48 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
+/* Decompresses every key and builds its comb table in HBM (window 17 bits: 94 MB, 16: 50 MB, 15: 27 MB, 14: 14 MB, 12: 4.1 MB per key).  out_valid_bitmap (nullable): bit i = key i
  * decompresses.  Replaces the per-call PublicKey::from_bytes of crypto/src/lib.rs:202,216. */
 int hs_committee_register(hs_ctx *ctx, const uint8_t *pks /* N x 32 */, size_t N, uint32_t *out_valid_bitmap);
 /* Incremental epoch change: validators remove_idx[] stop verifying (their indices become free), keys add_pks[] take a free
