@@ -13,8 +13,10 @@
  *   strict: R must decompress, R and A must not be small order, k = SHA512(R||A||M) mod l,
  *           accept iff [S]B + [k](-A) == R as projective points (no cofactor).
  *
- * Pinning: RFC 8032 §7.1 vectors, FIPS 180-4 vectors, OpenSSL and libsodium cross-checks, and the
- * fixtures derived from the reference's own tests — see tests/test_oracle_pins.py.
+ * PARITY UNPINNED (in the task's strict sense): the reference holds no golden vectors for this path and dalek cannot be
+ * built or run here (no Rust toolchain, crate not vendored).  What the oracle IS pinned on: RFC 8032 §7.1 vectors, FIPS 180-4
+ * vectors, OpenSSL and libsodium differentials, the fixtures derived from the reference's own tests, and
+ * dalek's PUBLISHED verdicts for the 12 ed25519-speccheck case classes — see tests/test_oracle_pins.py and oracle/README.md.
  *
  * Representation here is deliberately different from the CUDA code (5x51-bit limbs, __int128) so the
  * two implementations do not share bugs.

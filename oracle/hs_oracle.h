@@ -6,6 +6,9 @@
  * vendored under /root/reference and there is no Rust toolchain here, so this restates the
  * crate's published algorithm; see oracle/README.md for how it is pinned).
  *
+ * PARITY UNPINNED against a running dalek (cannot be built here); pinned on RFC 8032 / FIPS 180-4 known answers, OpenSSL + libsodium
+ * differentials, reference-derived fixtures and dalek's published speccheck verdicts (oracle/README.md).
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * link or call this. The product path (hotstuff_b200/ + include/hs_crypto.h) never does.
  */
