@@ -777,6 +777,7 @@ struct hs_ctx {
   uint8_t *d_learn_keys = nullptr, *h_learn_keys = nullptr;
   uint32_t *d_learn_n = nullptr, *h_learn_n = nullptr;
   cudaEvent_t ev_learn = nullptr;
+  cudaEvent_t ev_tables = nullptr;   // recorded after the latest table build of the key cache; every pass waits for it (any stream)
   bool learn_pending = false;
   bool cache_full = false;           // no free slot: only the miss RATE is watched (a mostly-missing full cache is reset)
   uint64_t calls_since_reset = HS_CACHE_RESET_MIN_CALLS;
@@ -975,6 +976,7 @@ static int learn_process(hs_ctx *c, cudaStream_t stream) {
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
   // (no synchronisation: copies from pageable memory return once the source is staged, so the host vectors may change afterwards)
+  HS_CUDA(c, cudaEventRecord(c->ev_tables, stream));  // passes on OTHER streams (host entry points vs a _dev caller's stream) wait for the build
   c->n_keys = old_n + n_new;
   if (c->n_keys >= c->cache_cap) c->cache_full = true;  // no free slot: unknown keys stay on the generic path until a reset
   return HS_OK;
@@ -989,6 +991,7 @@ static int learn_collect(hs_ctx *c, const in_layout &L, size_t n, bool have_look
     HS_CUDA(c, cudaMallocHost(&c->h_learn_n, 4));
     HS_CUDA(c, cudaMallocHost(&c->h_miss_total, 4));
     HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_learn, cudaEventDisableTiming));
+    HS_CUDA(c, cudaEventCreateWithFlags(&c->ev_tables, cudaEventDisableTiming));
   }
   c->learn_records = n;
   if (c->cache_full) {  // only watch the miss rate
@@ -1024,6 +1027,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   }
   if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (!indexed) HS_TRY(learn_process(c, stream));
+  if (c->ev_tables && !c->explicit_committee) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_tables, 0));
   dev_buf &XYZ = (c->deferred && c->flip) ? c->xyz2 : c->xyz, &META = (c->deferred && c->flip) ? c->meta2 : c->meta;
   const int set = c->deferred ? c->flip : 0;
   if (c->deferred) {
@@ -1120,6 +1124,7 @@ static int run_small(hs_ctx *c, size_t n, uint32_t mode, uint32_t *out_bitmap, u
   HS_CUDA(c, cudaHostGetDevicePointer(&d_done, c->h_small_done, 0));
   const uint32_t seq = ++c->small_seq ? c->small_seq : ++c->small_seq;  // never 0
   committee_tables C{c->d_pks, c->d_key_flags, (uint32_t)c->n_keys, c->d_atables, c->a_table_entries};
+  if (c->ev_tables && !c->explicit_committee) HS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tables, 0));
   k_verify_small<<<(unsigned)n, 64, 0, c->stream>>>(d_in, (uint32_t)n, c->d_btable, C, c->cp, d_out, c->d_small_counter, d_done, seq);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
@@ -1262,6 +1267,7 @@ void hs_ctx_destroy(hs_ctx *c) {
   if (c->h_learn_n) cudaFreeHost(c->h_learn_n);
   if (c->h_miss_total) cudaFreeHost(c->h_miss_total);
   if (c->ev_learn) cudaEventDestroy(c->ev_learn);
+  if (c->ev_tables) cudaEventDestroy(c->ev_tables);
   for (int i = 0; i < 2; i++)
     if (c->ev_prof[i]) cudaEventDestroy(c->ev_prof[i]);
   for (int p = 0; p < HS_MAX_PEERS; p++)
