@@ -375,6 +375,8 @@ def main():
                     help="comb window of the base-point table in bits: 24 = the library default (11 windows, 8.9 GB).  26 (10 windows, 32 GB: one "
                          "mixed addition fewer) was measured on B200 and buys nothing — 2.361 vs 2.371 ms for the main kernel — because the gathers "
                          "from the 3.6x larger table miss L2/TLB more often (profiles/r02_bench_base_window_26.json)")
+    ap.add_argument("--key-window", type=int, default=0, help="force the per-key comb window (bits); 0 = widest that fits the table budget. "
+                    "E.g. --base-window 20 --key-window 12 is the ~18 GB configuration for a shared GPU (DESIGN.md §5c)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling QC leg (BASELINE config[3]) reported next to the headline")
     ap.add_argument("--committee", type=int, default=1000)
     ap.add_argument("--qcs", type=int, default=10000)
@@ -399,7 +401,7 @@ def main():
     from hotstuff_b200 import Engine, build
     if not os.environ.get("HS_CRYPTO_LIB"):
         build.build_engine()
-    eng = Engine(local_rank, key_cache=(args.key_mode != "generic"), base_window=args.base_window)
+    eng = Engine(local_rank, key_cache=(args.key_mode != "generic"), base_window=args.base_window, key_window=args.key_window)
     n, L = args.n, args.msg_len
     inp = make_inputs(n, args.keys, L, seed=1234 + rank, corrupt_frac=0.01, engine=eng)
     n_bad = int(inp["corrupted"].sum())
