@@ -3,15 +3,21 @@
 // Hot path of asonnino/hotstuff's crypto crate (crypto/src/lib.rs:200-219 + the SHA-512 Digest call sites) rebuilt for
 // B200.  No CPU path: if CUDA fails the call returns an error and the caller must reject.
 //
-// Pipeline of one verify call:
+// Throughput pipeline of one verify call (any n):
 //   k_key_lookup      pk bytes -> committee index through a device hash table; misses -> compacted list
 //                     (skipped when the caller gives validator indices)
-//   k_verify_main<C>  registered keys: SHA-512(R||A||M) -> k mod l -> [k](-A) + [S]B by table gathers only
-//                     (e.g. 17 + 11 mixed additions for 4,096 keys; no doublings, no decompression) -> (X:Y:Z) + meta
-//   k_verify_main<G>  records whose key is not registered: decompress A, radix-16 window for [k](-A); runs over the
-//                     compacted list on a high-priority side stream, concurrently with the pass above
+//   k_verify_main<C>  registered / learned keys: SHA-512(R||A||M) -> k mod l -> [k](-A) + [S]B by table gathers only
+//                     (17 + 11 mixed additions for 4,096 keys; no doublings, no decompression) -> (X:Y:Z) + meta
+//   k_verify_main<G>  records whose key has no table: decompress A, radix-16 window for [k](-A); runs over the
+//                     compacted list on a high-priority side stream, beside the pass above
 //   k_verify_finish   two-level Montgomery-batched inversion, affine compare with R's encoding, small-order rule,
-//                     32 verdicts -> one bitmap word, stored locally or into every peer GPU's buffer (fused all-gather)
+//                     32 verdicts -> one bitmap word, stored locally or into every peer GPU's buffer (fused all-gather,
+//                     epoch flags exchanged by the last block); optionally on the context's tail stream (deferred mode)
+// Latency pipeline (n <= 64, every key has a table): k_verify_small — ONE launch, a warp per signature sums the table entries
+//   with a shuffle tree while a second warp decompresses R; inputs / verdicts in mapped pinned memory.
+// Digest: k_digest32_fixed (staged coalesced loads, constant padding schedule), k_digest32 (any length), k_digest32_long
+//   (one warp per long message, schedules expanded across lanes).
+// Front ends: QC / TC / Timeout / Block groups with on-GPU digests and per-certificate AND; load-generation keygen / signer.
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
