@@ -1034,9 +1034,10 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   if (indexed && (!c->explicit_committee || c->n_keys == 0)) return fail(c, HS_ERR_ARG, "committee-indexed verify without a registered committee");
   if (!indexed) HS_TRY(learn_process(c, stream));
   if (c->ev_tables && !c->explicit_committee) HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_tables, 0));
-  dev_buf &XYZ = (c->deferred && c->flip) ? c->xyz2 : c->xyz, &META = (c->deferred && c->flip) ? c->meta2 : c->meta;
-  const int set = c->deferred ? c->flip : 0;
-  if (c->deferred) {
+  const bool defer = c->deferred && stream != c->stream;  // host-pointer entry points (internal stream) always complete in stream order
+  dev_buf &XYZ = (defer && c->flip) ? c->xyz2 : c->xyz, &META = (defer && c->flip) ? c->meta2 : c->meta;
+  const int set = defer ? c->flip : 0;
+  if (defer) {
     c->flip ^= 1;
     HS_CUDA(c, cudaStreamWaitEvent(stream, c->ev_tail[set], 0));  // the finish kernel that last read this scratch set is done
   }
@@ -1084,7 +1085,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   }
   // small batches: small groups, so that enough blocks exist to hide each block's serial inversion; when the tail overlaps the next pass
   // (deferred mode) latency is hidden anyway and the 16-record group costs the fewest inversions
-  const int fin_group = (c->deferred || n >= (1u << 19)) ? 16 : (n >= (1u << 18) ? 8 : 4);
+  const int fin_group = (defer || n >= (1u << 19)) ? 16 : (n >= (1u << 18) ? 8 : 4);
   const size_t fin_threads = (n + fin_group - 1) / fin_group;
   peer_route P{};
   if (c->peer_armed) {
@@ -1092,7 +1093,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
     c->peer_armed = false;
   }
   cudaStream_t fin_stream = stream;
-  if (c->deferred) {  // tail on the internal stream: the caller's stream is free for the next pass's digest / main kernels
+  if (defer) {  // tail on the internal stream: the caller's stream is free for the next pass's digest / main kernels
     HS_CUDA(c, cudaEventRecord(c->ev_main_done, stream));
     HS_CUDA(c, cudaStreamWaitEvent(c->stream_tail, c->ev_main_done, 0));
     fin_stream = c->stream_tail;
@@ -1100,7 +1101,7 @@ static int run_verify(hs_ctx *c, in_layout L, size_t n, uint32_t mode, uint32_t 
   k_verify_finish<<<blocks_for(fin_threads), HS_THREADS, 0, fin_stream>>>(L, n, (const fe *)XYZ.p, (const uint8_t *)META.p, mode, d_bitmap, d_flags_out, P, fin_group);
   c->launches++;
   HS_CUDA(c, cudaGetLastError());
-  if (c->deferred) HS_CUDA(c, cudaEventRecord(c->ev_tail[set], c->stream_tail));
+  if (defer) HS_CUDA(c, cudaEventRecord(c->ev_tail[set], c->stream_tail));
   return HS_OK;
 }
 
@@ -1619,7 +1620,7 @@ int hs_verify_qc_votes_dev(hs_ctx *c, const void *d_qc_digests, const void *d_pk
 int hs_qc_and_dev(hs_ctx *c, const void *d_vote_bitmap, const void *d_qc_idx, size_t n_votes, size_t n_qc, void *d_qc_bitmap, void *stream) {
   if (!c || !d_qc_bitmap || (n_votes && (!d_vote_bitmap || !d_qc_idx))) return fail(c, HS_ERR_ARG, "hs_qc_and_dev: bad argument");
   HS_CUDA(c, cudaSetDevice(c->device));
-  cudaStream_t st = c->deferred ? c->stream_tail : (cudaStream_t)stream;  // deferred mode: ordered after the finish kernel on the tail stream
+  cudaStream_t st = (c->deferred && (cudaStream_t)stream != c->stream) ? c->stream_tail : (cudaStream_t)stream;  // deferred: after the finish kernel on the tail stream
   if (n_qc) k_bitmap_ones<<<blocks_for((n_qc + 31) / 32, 256), 256, 0, st>>>((uint32_t *)d_qc_bitmap, n_qc);
   if (n_votes)
     k_qc_and<<<blocks_for(n_votes, 256), 256, 0, st>>>((const uint32_t *)d_vote_bitmap, (const uint32_t *)d_qc_idx, n_votes, n_qc, (uint32_t *)d_qc_bitmap);

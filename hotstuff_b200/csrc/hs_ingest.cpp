@@ -305,6 +305,11 @@ bool parse_frame(const uint8_t *p, const uint8_t *end, sink &s, uint32_t group, 
 
 extern "C" int hs_ingest_consensus_frames(const uint8_t *frames, const uint64_t *off, size_t n, hs_frame_info *info, hs_ingest_out *out) {
   if (!out || (n && (!off || !info)) || (n && off[n] && !frames)) return HS_ERR_ARG;
+  if (n == 0) {
+    out->n_items = out->n_msgs = out->pre_bytes = 0;
+    if (out->pre_off) out->pre_off[0] = 0;
+    return HS_OK;
+  }
   if (out->cap_items && (!out->sig || !out->pk || !out->msg_idx || !out->group_idx || !out->mode)) return HS_ERR_ARG;
   if (out->cap_msgs && (!out->pre_off || (out->cap_pre_bytes && !out->preimages))) return HS_ERR_ARG;
   if (!out->pre_off) return HS_ERR_ARG;
