@@ -306,9 +306,10 @@ __global__ void __launch_bounds__(64) k_verify_small(const small_rec *__restrict
     load32(M, rec->msg);
     sha512_ram32(h, R, A, M);
     sc_reduce512(k, h);
-    // every lane computes the same digits and stores the same values
-    sc_digits_rt(dig, 1, k, cp.bias_a, cp.wa, cp.na);
-    sc_digits_rt(dig + cp.na, 1, S, cp.bias_b, cp.wb, cp.nb);
+    if (lane == 0) {  // one writer for the shared digit array
+      sc_digits_rt(dig, 1, k, cp.bias_a, cp.wa, cp.na);
+      sc_digits_rt(dig + cp.na, 1, S, cp.bias_b, cp.wb, cp.nb);
+    }
     __syncwarp();
     const int NT = cp.na + cp.nb;
     ge_ext acc;
