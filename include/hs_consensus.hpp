@@ -4,6 +4,7 @@
 // Same behaviour and error order as the reference; the signature work goes through the engine's batch front ends
 // (hs_verify_batch_shared_msg, hs_verify_qcs, hs_verify_tcs).  tests/cpp/consensus_tests.cpp ports messages_tests.rs.
 #pragma once
+#include <list>
 #include <map>
 #include <set>
 #include <string>
@@ -106,6 +107,54 @@ inline std::vector<bool> verify_qcs(const Engine &e, const Committee &c, const s
   return ok;
 }
 
+// Verified-QC cache: during a view change every Timeout carries its sender's high_qc, so a node re-verifies the same
+// certificate up to N times (core.rs:227 -> Timeout::verify -> QC::verify).  A hit requires the candidate's BYTES — (hash, round) and every
+// (name, signature) — to equal a certificate that already verified, so the verdict is exactly the reference's; bounded LRU keyed by (hash, round).
+class VerifiedQcCache {
+ public:
+  explicit VerifiedQcCache(size_t capacity = 1024) : cap_(capacity) {}
+  static std::vector<uint8_t> wire(const QC &q) {
+    std::vector<uint8_t> w(q.hash.bytes.begin(), q.hash.bytes.end());
+    uint8_t r[8];
+    put_le64(r, q.round);
+    w.insert(w.end(), r, r + 8);
+    for (auto &v : q.votes) {
+      w.insert(w.end(), v.first.bytes.begin(), v.first.bytes.end());
+      const auto f = v.second.flatten();
+      w.insert(w.end(), f.begin(), f.end());
+    }
+    return w;
+  }
+  bool known_valid(const QC &q) {
+    auto it = map_.find(key(q));
+    if (it == map_.end() || it->second->second != wire(q)) {
+      misses++;
+      return false;
+    }
+    lru_.splice(lru_.begin(), lru_, it->second);
+    hits++;
+    return true;
+  }
+  void remember(const QC &q) {
+    auto it = map_.find(key(q));
+    if (it != map_.end()) lru_.erase(it->second);
+    lru_.emplace_front(key(q), wire(q));
+    map_[key(q)] = lru_.begin();
+    while (lru_.size() > cap_) {
+      map_.erase(lru_.back().first);
+      lru_.pop_back();
+    }
+  }
+  size_t hits = 0, misses = 0;
+
+ private:
+  using Key = std::pair<std::array<uint8_t, 32>, Round>;
+  static Key key(const QC &q) { return {q.hash.bytes, q.round}; }
+  size_t cap_;
+  std::list<std::pair<Key, std::vector<uint8_t>>> lru_;
+  std::map<Key, std::list<std::pair<Key, std::vector<uint8_t>>>::iterator> map_;
+};
+
 struct TC {  // messages.rs:283-287
   Round round = 0;
   std::vector<std::tuple<PublicKey, Signature, Round>> votes;
@@ -169,5 +218,69 @@ struct Timeout {  // messages.rs:223-228
     if (!high_qc.is_genesis()) high_qc.verify(e, c);
   }
 };
+
+// Timeout::verify for a burst (core.rs:227: one timeout per validator during a view change): the n author signatures in ONE hs_verify_tcs
+// call (digests built on the GPU), the embedded high_qcs — mostly the same certificate n times — through verify_qcs with the exact-match
+// cache.  Returns "" (valid) or the name of the ConsensusError the reference raises first, per timeout.
+inline std::vector<std::string> verify_timeouts(const Engine &e, const Committee &c, const std::vector<Timeout> &ts, VerifiedQcCache &cache) {
+  std::vector<std::string> out(ts.size());
+  std::vector<uint64_t> rounds, hq;
+  std::vector<uint8_t> pk, sig;
+  std::vector<size_t> live;
+  for (size_t j = 0; j < ts.size(); j++) {
+    if (c.stake(ts[j].author) == 0) {
+      out[j] = "UnknownAuthority";
+      continue;
+    }
+    rounds.push_back(ts[j].round);
+    hq.push_back(ts[j].high_qc.round);
+    pk.insert(pk.end(), ts[j].author.bytes.begin(), ts[j].author.bytes.end());
+    const auto f = ts[j].signature.flatten();
+    sig.insert(sig.end(), f.begin(), f.end());
+    live.push_back(j);
+  }
+  if (live.empty()) return out;
+  std::vector<uint32_t> bm((live.size() + 31) / 32 + 1);
+  e.check(hs_verify_tcs(e.raw(), rounds.data(), live.size(), pk.data(), nullptr, sig.data(), hq.data(), nullptr, live.size(), nullptr, bm.data()), "hs_verify_tcs");
+  std::vector<QC> todo;
+  std::vector<size_t> todo_of;       // timeout index of each certificate still to verify
+  std::vector<std::pair<size_t, size_t>> alias;  // (timeout, index into todo) for byte-identical certificates inside this burst
+  for (size_t k = 0; k < live.size(); k++) {
+    const size_t j = live[k];
+    if (!((bm[k / 32] >> (k % 32)) & 1u)) {
+      out[j] = "InvalidSignature";
+      continue;
+    }
+    const QC &q = ts[j].high_qc;
+    if (q.is_genesis()) continue;
+    try {
+      q.check_quorum(c);
+    } catch (const ConsensusError &ex) {
+      out[j] = ex.what();
+      continue;
+    }
+    if (cache.known_valid(q)) continue;
+    const auto w = VerifiedQcCache::wire(q);
+    size_t same = todo.size();
+    for (size_t t = 0; t < todo.size(); t++)
+      if (VerifiedQcCache::wire(todo[t]) == w) same = t;
+    if (same < todo.size()) {
+      alias.push_back({j, same});
+    } else {
+      todo.push_back(q);
+      todo_of.push_back(j);
+    }
+  }
+  if (!todo.empty()) {
+    const auto ok = verify_qcs(e, c, todo);
+    for (size_t t = 0; t < todo.size(); t++) {
+      if (ok[t]) cache.remember(todo[t]);
+      else out[todo_of[t]] = "InvalidSignature";
+    }
+    for (auto &a : alias)
+      if (!ok[a.second]) out[a.first] = "InvalidSignature";
+  }
+  return out;
+}
 
 }  // namespace hs

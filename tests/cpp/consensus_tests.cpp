@@ -85,6 +85,22 @@ int main(int argc, char **argv) {
   t.verify(e, c);
   t.high_qc.votes[0].second = hs::Signature{};
   REQUIRE(error_of([&] { t.verify(e, c); }) == "InvalidSignature");
+  {  // view-change burst: four timeouts with the SAME high_qc + one whose certificate differs in one vote: the shared one is verified once
+    t.high_qc = qc;
+    std::vector<hs::Timeout> burst(4, t);
+    hs::Timeout forged = t;
+    forged.high_qc.votes[2].second = hs::Signature{};
+    burst.push_back(forged);
+    hs::VerifiedQcCache cache;
+    const uint64_t l0 = hs_kernel_launches(e.raw());
+    auto res = hs::verify_timeouts(e, c, burst, cache);
+    REQUIRE(res == (std::vector<std::string>{"", "", "", "", "InvalidSignature"}));
+    const uint64_t first = hs_kernel_launches(e.raw()) - l0;
+    res = hs::verify_timeouts(e, c, std::vector<hs::Timeout>(burst.begin(), burst.begin() + 4), cache);
+    REQUIRE(res == (std::vector<std::string>(4, "")) && cache.hits >= 4);
+    REQUIRE(hs_kernel_launches(e.raw()) - l0 - first < first);  // all four certificates came from the cache: only the timeout signatures ran
+    REQUIRE(hs::verify_timeouts(e, c, {forged}, cache)[0] == "InvalidSignature");  // a hit needs identical bytes
+  }
   hs::TC tc;
   tc.round = 7;
   const uint64_t hqs[3] = {3, 5, 4};
