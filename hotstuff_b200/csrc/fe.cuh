@@ -66,7 +66,11 @@ HS_HD void fe_mul_c(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b
 HS_HD void fe_mul(fe &r, const fe &a, const fe &b) {
 #if defined(__CUDA_ARCH__)
   uint32_t t[8];
+#if defined(HS_FE_KARATSUBA)
+  fe_mul_karatsuba_asm(t, a.v, b.v);  // experiment: 56 wide multiplies + ~117 ALU ops instead of 72 + 37
+#else
   fe_mul_asm(t, a.v, b.v);
+#endif
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = t[i];
 #else

@@ -254,6 +254,96 @@ def gen_mul():
     return pr
 
 
+def prod4(pr, x, y, tag, out):
+    """out[0..7] = x[0..3] * y[0..3] (4 x 4 limbs) through the same even/odd accumulator arrays as the 8 x 8 product (every lo/hi pair
+    fuses to one IMAD.WIDE.U32[.X]); the two arrays are merged into eight plain limbs at the end."""
+    class EN:
+        def __mod__(self, k):
+            return "%se%d" % (tag, k)
+    class ON:
+        def __mod__(self, k):
+            return "%so%d" % (tag, k)
+    E, O = EN(), ON()
+    de, do = set(), set()
+    for i in range(4):
+        te = [(i + j, y[j]) for j in range(4) if (i + j) % 2 == 0]
+        to = [(i + j - 1, y[j]) for j in range(4) if (i + j) % 2 == 1]
+        if i == 0:
+            for lo, bj in te:
+                pr.emit("mul.lo.u32", E % lo, x[0], bj); pr.emit("mul.hi.u32", E % (lo + 1), x[0], bj)
+                de |= {lo, lo + 1}
+            for lo, bj in to:
+                pr.emit("mul.lo.u32", O % lo, x[0], bj); pr.emit("mul.hi.u32", O % (lo + 1), x[0], bj)
+                do |= {lo, lo + 1}
+            continue
+        chain_row(pr, E, de, x[i], te, 8)
+        chain_row(pr, O, do, x[i], to, 7)
+    assert de == set(range(8)) and do == set(range(7)), (de, do)
+    pr.emit("add.u32", out[0], E % 0, 0)
+    pr.emit("add.cc.u32", out[1], E % 1, O % 0)
+    for k in range(2, 7):
+        pr.emit("addc.cc.u32", out[k], E % k, O % (k - 1))
+    pr.emit("addc.u32", out[7], E % 7, O % 6)
+
+
+def gen_mul_karatsuba():
+    """One level of Karatsuba on 4-limb halves: 3 x 16 = 48 wide multiplies instead of 64 (+ 8 for the fold), paid for with ~80 more
+    adds / subtracts on the ALU pipe — the pipe that has slack in k_verify_main (31 % busy against 83 % for the multiply pipe).
+    MEASURED AND NOT KEPT (round 2): correct (simulation + GPU parity), but the mixed-addition loop grows from 1,120 to 1,562 SASS
+    instructions (the three short products triple the carry materialisations: 164 IMAD.MOV + 157 SEL) and k_verify_main takes
+    2.44 ms instead of 2.26 ms per 2^20.  Emitted into fe_asm.cuh only with HS_GEN_KARATSUBA=1 (fe.cuh: -DHS_FE_KARATSUBA)."""
+    pr = Prog()
+    a = ["a%d" % i for i in range(8)]
+    b = ["b%d" % i for i in range(8)]
+    sa, sb = ["sa%d" % i for i in range(4)], ["sb%d" % i for i in range(4)]
+    for s_, x, c in ((sa, a, "ca"), (sb, b, "cb")):
+        pr.emit("add.cc.u32", s_[0], x[0], x[4])
+        for k in range(1, 4):
+            pr.emit("addc.cc.u32", s_[k], x[k], x[k + 4])
+        pr.emit("addc.u32", c, 0, 0)
+    p0 = ["r0", "r1", "r2", "r3", "p04", "p05", "p06", "p07"]
+    p2 = ["p2%d" % k for k in range(8)]
+    pm = ["pm%d" % k for k in range(9)]
+    prod4(pr, a[:4], b[:4], "x", p0)
+    prod4(pr, a[4:], b[4:], "y", p2)
+    prod4(pr, sa, sb, "z", pm[:8])
+    # (sa + ca 2^128)(sb + cb 2^128) = pm + (ca sb + cb sa) 2^128 + ca cb 2^256
+    pr.emit("sub.u32", "ma", 0, "ca")
+    pr.emit("sub.u32", "mb", 0, "cb")
+    for k in range(4):
+        pr.emit("and", "ta%d" % k, sb[k], "ma")
+        pr.emit("and", "tb%d" % k, sa[k], "mb")
+    pr.emit("add.cc.u32", pm[4], pm[4], "ta0")
+    for k in range(1, 4):
+        pr.emit("addc.cc.u32", pm[4 + k], pm[4 + k], "ta%d" % k)
+    pr.emit("addc.u32", pm[8], 0, 0)
+    pr.emit("add.cc.u32", pm[4], pm[4], "tb0")
+    for k in range(1, 4):
+        pr.emit("addc.cc.u32", pm[4 + k], pm[4 + k], "tb%d" % k)
+    pr.emit("addc.u32", pm[8], pm[8], 0)
+    pr.emit("and", "cab", "ca", "cb")
+    pr.emit("add.u32", pm[8], pm[8], "cab")
+    # middle term = that - p0 - p2 (non-negative, < 2^258)
+    for sub in (p0, p2):
+        pr.emit("sub.cc.u32", pm[0], pm[0], sub[0])
+        for k in range(1, 8):
+            pr.emit("subc.cc.u32", pm[k], pm[k], sub[k])
+        pr.emit("subc.u32", pm[8], pm[8], 0)
+    # c[0..15] = p0 + middle 2^128 + p2 2^256
+    c = ["r%d" % k for k in range(8)] + ["c%d" % k for k in range(8, 16)]
+    pr.emit("add.cc.u32", c[4], p0[4], pm[0])
+    for k in range(1, 4):
+        pr.emit("addc.cc.u32", c[4 + k], p0[4 + k], pm[k])
+    for k in range(4):
+        pr.emit("addc.cc.u32", c[8 + k], p2[k], pm[4 + k])
+    pr.emit("addc.cc.u32", c[12], p2[4], pm[8])
+    pr.emit("addc.cc.u32", c[13], p2[5], 0)
+    pr.emit("addc.cc.u32", c[14], p2[6], 0)
+    pr.emit("addc.u32", c[15], p2[7], 0)
+    gen_reduce(pr, c, c[:8])
+    return pr
+
+
 def gen_sqr(split=True):
     pr = Prog()
     a = ["a%d" % i for i in range(8)]
@@ -493,6 +583,8 @@ def count(pr):
 
 if __name__ == "__main__":
     m, s = gen_mul(), gen_sqr(split=os.environ.get('HS_SQR_SPLIT', '0') == '1')
+    mk = gen_mul_karatsuba()   # experiment (measured slower on B200: profiles/r02_variants_karatsuba_NOT_KEPT.txt); emitted only on request
+    check(mk, False)
     check(m, False)
     check(s, True)
     check_reduce()
@@ -503,8 +595,8 @@ if __name__ == "__main__":
            "// GF(2^255-19) multiply / square on 8 saturated 32-bit limbs; mad.lo.cc/madc.hi.cc pairs fuse to IMAD.WIDE.U32.X.\n"
            "// Every sequence below was simulated against Python big integers by the generator before being emitted.\n"
            "#pragma once\n#include <cstdint>\n\n")
-    txt = (hdr + emit_function("fe_mul_asm", m, 2) + "\n" + emit_function("fe_sqr_asm", s, 1) + "\n" +
+    txt = (hdr + emit_function("fe_mul_asm", m, 2) + "\n" + (emit_function("fe_mul_karatsuba_asm", mk, 2) + "\n" if os.environ.get("HS_GEN_KARATSUBA") == "1" else "") + emit_function("fe_sqr_asm", s, 1) + "\n" +
            emit_function("fe_add_asm", ad, 2) + "\n" + emit_function("fe_sub_asm", sb, 2))
     path = os.path.join(ROOT, "hotstuff_b200", "csrc", "fe_asm.cuh")
     open(path, "w").write(txt)
-    print("mul: %d wide-mads + %d other ops; sqr: %d wide-mads + %d other ops -> %s" % (count(m) + count(s) + (path,)))
+    print("mul: %d wide-mads + %d other ops; karatsuba mul: %d + %d; sqr: %d wide-mads + %d other ops -> %s" % (count(m) + count(mk) + count(s) + (path,)))
