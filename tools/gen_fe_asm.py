@@ -582,7 +582,7 @@ def count(pr):
 
 
 if __name__ == "__main__":
-    m, s = gen_mul(), gen_sqr(split=os.environ.get('HS_SQR_SPLIT', '0') == '1')
+    m, s = gen_mul(), gen_sqr(split=os.environ.get('HS_SQR_SPLIT', '1') == '1')
     mk = gen_mul_karatsuba()   # experiment (measured slower on B200: profiles/r02_variants_karatsuba_NOT_KEPT.txt); emitted only on request
     check(mk, False)
     check(m, False)
