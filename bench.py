@@ -591,7 +591,7 @@ def main():
         dom_ms = main_ms if main_ms and main_ms > 0 else kern_ms
         achieved = ALGO_BYTES_VERIFY * n / (dom_ms * 1e-3) / 1e9
         # dram__bytes_read + dram__bytes_write and pipe utilisation of the kernels from THIS round's ncu --set full capture at the same
-        # 2^20 records per launch (tools/r2_pass2.sh -> tools/ncu_traffic.py -> profiles/r02_traffic.json); not measured in this run
+        # 2^20 records per launch (tools/run_all_gpu.sh -> tools/ncu_traffic.py -> profiles/r02_traffic.json); not measured in this run
         tr = {}
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
