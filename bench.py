@@ -361,7 +361,7 @@ def main():
                          "engine resolves through its device hash table.  indexed: records carry validator indices.  generic: nothing registered, "
                          "every key is decompressed per record (key cache off).  cache: nothing registered, the engine learns the keys during warm-up")
     ap.add_argument("--ref-sample", type=int, default=1 << 18)
-    ap.add_argument("--cpu-sample", type=int, default=1 << 17)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-pointer leg")
     ap.add_argument("--workload", default="msgs", choices=["msgs", "qc"],
