@@ -37,8 +37,38 @@ RUST_TO_C = {
     "*const u8": "const uint8_t*", "*mut u8": "uint8_t*", "*const u32": "const uint32_t*", "*mut u32": "uint32_t*",
     "*const u64": "const uint64_t*", "*mut c_int": "int*", "*mut HsCtx": "hs_ctx*", "*const HsCtx": "const hs_ctx*",
     "*mut *mut HsCtx": "hs_ctx**", "*const HsRec128": "const hs_rec128*", "*const HsVote": "const hs_vote*",
-    "*const std::os::raw::c_char": "const char*",
+    "*const std::os::raw::c_char": "const char*", "*mut HsFrameInfo": "hs_frame_info*", "*mut HsIngestOut": "hs_ingest_out*",
 }
+RUST_SIZES = {"u8": 1, "u32": 4, "u64": 8, "usize": 8, "*mut u8": 8, "*mut u32": 8, "*mut u64": 8}
+C_SIZES = {"uint8_t": 1, "uint32_t": 4, "uint64_t": 8, "size_t": 8, "uint8_t*": 8, "uint32_t*": 8, "uint64_t*": 8}
+
+
+def _c_struct_fields(hdr, name):
+    body = re.search(r"typedef struct\s*(?:\w+\s*)?\{([^}]*)\}\s*%s\s*;" % name, hdr).group(1)
+    fields = []
+    for decl in [d.strip() for d in body.split(";") if d.strip()]:
+        m = re.match(r"^(\w+)\s+(.*)$", decl)
+        for var in m.group(2).split(","):
+            var = var.strip()
+            fields.append((var.lstrip("*"), m.group(1) + ("*" if var.startswith("*") else "")))
+    return fields
+
+
+def _rust_struct_fields(src, name):
+    body = re.search(r"pub struct %s\s*\{(.*?)\}" % name, src, flags=re.S).group(1)
+    return [(m.group(1), re.sub(r"\s+", " ", m.group(2).strip())) for m in re.finditer(r"pub (\w+):\s*([^,}]+)", body)]
+
+
+def test_rust_shim_ingest_structs_match_the_header_field_by_field():
+    src = _strip_comments(open(os.path.join(ROOT, "rust", "crypto_gpu_shim.rs")).read())
+    hdr = _strip_comments(open(os.path.join(ROOT, "include", "hs_crypto.h")).read())
+    for rust_name, c_name, size in (("HsFrameInfo", "hs_frame_info", 48), ("HsIngestOut", "hs_ingest_out", 13 * 8)):
+        rf, cf = _rust_struct_fields(src, rust_name), _c_struct_fields(hdr, c_name)
+        assert [f for f, _ in rf] == [f for f, _ in cf], (rust_name, rf, cf)
+        assert [RUST_SIZES[t] for _, t in rf] == [C_SIZES[t] for _, t in cf], (rust_name, rf, cf)
+        assert sum(RUST_SIZES[t] for _, t in rf) == size       # no implicit padding: fields are laid out in non-increasing alignment groups
+    assert re.search(r"#define HS_FRAME_MALFORMED 255", hdr) and "pub const HS_FRAME_MALFORMED: u8 = 255;" in src
+    assert re.search(r"#define HS_ERR_NOMEM 3", hdr) and "pub const HS_ERR_NOMEM: c_int = 3;" in src
 
 
 def test_header_parser_sees_the_whole_abi():
@@ -64,7 +94,7 @@ def test_rust_shim_extern_block_matches_the_header():
             assert RUST_TO_C[r] == c, "%s parameter %d: shim %r vs header %r" % (name, k, r, c)
         assert RUST_TO_C[ret] == c_ret, "%s: return type" % name
         seen += 1
-    assert seen >= 9
+    assert seen >= 11
     # #[repr(C)] structs: field sizes add up to the C structs' sizes
     assert "pub struct HsRec128 { pub sig: [u8; 64], pub pk: [u8; 32], pub msg: [u8; 32] }" in src      # hs_rec128: 128 bytes
     assert "pub struct HsVote   { pub pk: [u8; 32], pub sig: [u8; 64] }" in src                          # hs_vote: 96 bytes
