@@ -2,7 +2,9 @@
 // layouts, the verify() pre-checks that decide what reaches the engine, and their error names (consensus/src/error.rs).
 //   Committee (config.rs:28-72), QC (messages.rs:165-208), TC (:283-315), Vote (:104-156), Timeout (:223-275).
 // Same behaviour and error order as the reference; the signature work goes through the engine's batch front ends
-// (hs_verify_batch_shared_msg, hs_verify_qcs, hs_verify_tcs).  tests/cpp/consensus_tests.cpp ports messages_tests.rs.
+// (hs_verify_batch_shared_msg, hs_verify_qcs, hs_verify_tcs), and the receiver path — bincode frames in, one verdict per frame out —
+// through hs_ingest_consensus_frames + hs_verify_groups (verify_frames).  tests/cpp/consensus_tests.cpp ports messages_tests.rs;
+// tests/cpp/frames_host_test.cpp runs verify_frames' host logic on a CPU box.
 #pragma once
 #include <list>
 #include <map>
@@ -281,6 +283,180 @@ inline std::vector<std::string> verify_timeouts(const Engine &e, const Committee
       if (!ok[a.second]) out[a.first] = "InvalidSignature";
   }
   return out;
+}
+
+// ---- receiver side (consensus/src/consensus.rs:33-39,138): bincode ConsensusMessage frames -> one verdict per frame ----------------
+// What the reference does per frame — bincode::deserialize, then Block / Vote / Timeout / TC::verify with their stake, duplicate and
+// quorum pre-checks (messages.rs:54-76,136-156,250-275,290-315) — for MANY frames with ONE engine pass: hs_ingest_consensus_frames lays
+// every signature out as an item of group (= frame) i, the pre-checks below run on the item ranges and decide which items are judged at
+// all, hs_verify_groups hashes every preimage and verifies every kept item on the GPU, and the per-frame result is the error the
+// reference would have raised FIRST ("" = Ok, "Malformed" = the SerializationError the receiver logs and drops).
+// (Same host logic as hotstuff_b200/wire.py::verify_frames, which the tests hold against struct-level verification.)
+struct IngestedFrames {
+  std::vector<hs_frame_info> info;
+  std::vector<uint8_t> sig, pk, mode, preimages;
+  std::vector<uint32_t> msg_idx, group_idx;
+  std::vector<uint64_t> pre_off;
+  size_t n_items() const { return msg_idx.size(); }
+};
+inline IngestedFrames ingest_frames(const std::vector<std::vector<uint8_t>> &frames) {
+  const size_t n = frames.size();
+  std::vector<uint64_t> off(n + 1, 0);
+  std::vector<uint8_t> blob;
+  for (size_t i = 0; i < n; i++) {
+    blob.insert(blob.end(), frames[i].begin(), frames[i].end());
+    off[i + 1] = blob.size();
+  }
+  if (blob.empty()) blob.push_back(0);
+  IngestedFrames g;
+  g.info.resize(n ? n : 1);
+  // every item costs >= 116 frame bytes, every preimage is copied from frame bytes: generous first guess, exact retry on HS_ERR_NOMEM
+  size_t ci = blob.size() / 116 + n + 1, cm = blob.size() / 60 + n + 1, cp = blob.size() + 64 * n + 64;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    g.sig.assign(ci * 64, 0);
+    g.pk.assign(ci * 32, 0);
+    g.mode.assign(ci, 0);
+    g.msg_idx.assign(ci, 0);
+    g.group_idx.assign(ci, 0);
+    g.preimages.assign(cp, 0);
+    g.pre_off.assign(cm + 1, 0);
+    hs_ingest_out o{};
+    o.cap_items = ci;
+    o.cap_msgs = cm;
+    o.cap_pre_bytes = cp;
+    o.sig = g.sig.data();
+    o.pk = g.pk.data();
+    o.msg_idx = g.msg_idx.data();
+    o.group_idx = g.group_idx.data();
+    o.mode = g.mode.data();
+    o.preimages = g.preimages.data();
+    o.pre_off = g.pre_off.data();
+    const int rc = hs_ingest_consensus_frames(blob.data(), off.data(), n, g.info.data(), &o);
+    if (rc == HS_OK) {
+      g.sig.resize(o.n_items * 64);
+      g.pk.resize(o.n_items * 32);
+      g.mode.resize(o.n_items);
+      g.msg_idx.resize(o.n_items);
+      g.group_idx.resize(o.n_items);
+      g.preimages.resize(o.pre_bytes);
+      g.pre_off.resize(o.n_msgs + 1);
+      g.info.resize(n);
+      return g;
+    }
+    if (rc != HS_ERR_NOMEM) throw EngineError("hs_ingest_consensus_frames: bad argument");
+    ci = o.n_items + 1;
+    cm = o.n_msgs + 1;
+    cp = o.pre_bytes + 1;
+  }
+  throw EngineError("hs_ingest_consensus_frames: capacity retry failed");
+}
+
+// `verify_items(g) -> std::vector<bool>` judges every item of g (already reduced to the items that passed the pre-checks): the engine
+// in production (verify_frames below); the tests substitute a CPU checker to run this host logic without a GPU.
+template <class ItemVerifier>
+inline std::vector<std::string> verify_frames_with(const Committee &c, const std::vector<std::vector<uint8_t>> &frames, ItemVerifier &&verify_items) {
+  IngestedFrames g = ingest_frames(frames);
+  const size_t n = frames.size(), items = g.n_items();
+  std::vector<std::string> out(n), qc_err(n), tc_err(n);
+  std::vector<char> skip(items, 0), decided(n, 0);
+  auto key_of = [&](size_t i) {
+    std::array<uint8_t, 32> k;
+    std::memcpy(k.data(), g.pk.data() + i * 32, 32);
+    return k;
+  };
+  auto stake_of = [&](size_t i) {
+    auto it = c.stakes.find(key_of(i));
+    return it == c.stakes.end() ? (Stake)0 : it->second;
+  };
+  auto quorum = [&](uint32_t lo, uint32_t hi, const char *err) -> std::string {  // messages.rs:182-194 / :292-304
+    Stake weight = 0;
+    std::set<std::array<uint8_t, 32>> used;
+    for (uint32_t i = lo; i < hi; i++) {
+      if (!used.insert(key_of(i)).second) return "AuthorityReuse";
+      const Stake st = stake_of(i);
+      if (st == 0) return "UnknownAuthority";
+      weight += st;
+    }
+    return weight >= c.quorum_threshold() ? "" : err;
+  };
+  auto skip_range = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; i++) skip[i] = 1;
+  };
+  for (size_t j = 0; j < n; j++) {
+    const hs_frame_info &f = g.info[j];
+    if (f.kind == HS_FRAME_MALFORMED) {
+      out[j] = "Malformed";
+      decided[j] = 1;
+      continue;
+    }
+    if (f.author_item != HS_NO_ITEM && stake_of(f.author_item) == 0) {  // ensure!(voting_power > 0, UnknownAuthority) comes first
+      out[j] = "UnknownAuthority";
+      decided[j] = 1;
+      skip_range(f.qc_lo, f.qc_hi);
+      skip_range(f.tc_lo, f.tc_hi);
+      skip[f.author_item] = 1;
+      continue;
+    }
+    if ((f.kind == 0 || f.kind == 2) && !f.qc_is_genesis) {  // Propose / Timeout carry a QC; genesis is not verified (messages.rs:67,261)
+      qc_err[j] = quorum(f.qc_lo, f.qc_hi, "QCRequiresQuorum");
+      if (!qc_err[j].empty()) {
+        skip_range(f.qc_lo, f.qc_hi);
+        skip_range(f.tc_lo, f.tc_hi);
+      }
+    }
+    if (f.has_tc && qc_err[j].empty()) {
+      tc_err[j] = quorum(f.tc_lo, f.tc_hi, "TCRequiresQuorum");
+      if (!tc_err[j].empty()) skip_range(f.tc_lo, f.tc_hi);
+    }
+  }
+  // one pass over the items that are still to be judged
+  IngestedFrames kept;
+  std::vector<size_t> kept_of;
+  for (size_t i = 0; i < items; i++) {
+    if (skip[i]) continue;
+    kept_of.push_back(i);
+    kept.sig.insert(kept.sig.end(), g.sig.begin() + i * 64, g.sig.begin() + (i + 1) * 64);
+    kept.pk.insert(kept.pk.end(), g.pk.begin() + i * 32, g.pk.begin() + (i + 1) * 32);
+    kept.mode.push_back(g.mode[i]);
+    kept.msg_idx.push_back(g.msg_idx[i]);
+    kept.group_idx.push_back(g.group_idx[i]);
+  }
+  kept.preimages = g.preimages;
+  kept.pre_off = g.pre_off;
+  kept.info = g.info;
+  std::vector<char> ok(items, 0);
+  if (!kept_of.empty()) {
+    const std::vector<bool> got = verify_items(kept);
+    if (got.size() != kept_of.size()) throw EngineError("verify_frames: item verifier returned the wrong number of verdicts");
+    for (size_t k = 0; k < kept_of.size(); k++) ok[kept_of[k]] = got[k] ? 1 : 0;
+  }
+  auto all_ok = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; i++)
+      if (!ok[i]) return false;
+    return true;
+  };
+  for (size_t j = 0; j < n; j++) {
+    const hs_frame_info &f = g.info[j];
+    if (decided[j] || f.kind == 4) continue;  // SyncRequest: nothing to verify
+    if (f.author_item != HS_NO_ITEM && !ok[f.author_item]) out[j] = "InvalidSignature";
+    else if (!qc_err[j].empty()) out[j] = qc_err[j];
+    else if (!all_ok(f.qc_lo, f.qc_hi)) out[j] = "InvalidSignature";
+    else if (!tc_err[j].empty()) out[j] = tc_err[j];
+    else if (!all_ok(f.tc_lo, f.tc_hi)) out[j] = "InvalidSignature";
+  }
+  return out;
+}
+inline std::vector<std::string> verify_frames(const Engine &e, const Committee &c, const std::vector<std::vector<uint8_t>> &frames) {
+  return verify_frames_with(c, frames, [&](const IngestedFrames &k) {
+    const size_t ni = k.n_items(), ng = k.info.size();
+    std::vector<uint32_t> item_bits((ni + 31) / 32 + 1, 0), group_bits((ng + 31) / 32 + 1, 0);
+    e.check(hs_verify_groups(e.raw(), k.preimages.data(), k.pre_off.data(), k.pre_off.size() - 1, k.sig.data(), k.pk.data(), nullptr, k.msg_idx.data(),
+                             k.group_idx.data(), k.mode.data(), ni, ng, item_bits.data(), group_bits.data()),
+            "hs_verify_groups");
+    std::vector<bool> got(ni);
+    for (size_t i = 0; i < ni; i++) got[i] = (item_bits[i / 32] >> (i % 32)) & 1u;
+    return got;
+  });
 }
 
 }  // namespace hs

@@ -55,3 +55,53 @@ def test_cpp_port_of_reference_messages_tests(oracle, golden):
         args.append(oracle.sign(seeds[i], oracle.digest32((7).to_bytes(8, "little") + hq.to_bytes(8, "little"))).hex())
     out = subprocess.run([_build("consensus_tests")] + args, capture_output=True, text=True)
     assert out.returncode == 0 and "cpp consensus mirror ok" in out.stdout, out.stderr + out.stdout
+
+
+def test_cpp_verify_frames_host_logic_matches_the_python_mirror(oracle, golden, tmp_path):
+    """hs::verify_frames (C++: ingest -> pre-checks -> one grouped pass -> first error per frame) on the frames of test_wire_ingest plus
+    malformed ones, with the CPU oracle standing in for the engine (test only): same outcome per frame as wire.verify_frames, which is
+    itself held against struct-level verification.  Also checks that items of certificates that fail a pre-check are never judged."""
+    import struct
+    import bincode_ref as bc
+    import messages_scenarios as sc
+    from hotstuff_b200 import build, crypto, messages, wire
+    fx = sc.Fixtures(oracle, golden, sc.OracleStubEngine(oracle))
+    chain = fx.chain(4)
+    blk_tc = fx.block(1, 9, qc=chain[3].qc, tc=fx.tc(8), payload=[fx.d(b"p1"), fx.d(b"p2")])
+    v = messages.Vote(fx.d(chain[0].preimage()), 1, fx.pks[3], crypto.Signature())
+    v.signature = fx.sign(3, fx.d(messages.vote_preimage(v.hash, v.round)))
+    to = fx.timeout(2, 9, chain[2].qc)
+    to_gen = fx.timeout(1, 4, messages.QC.genesis())
+    bad_sig = fx.block(2, 6, qc=chain[2].qc)
+    bad_sig.round = 7
+    reuse = fx.block(0, 6, qc=fx.qc_for(fx.d(b"y"), 5))
+    reuse.qc.votes[1] = reuse.qc.votes[0]
+    bad_qc_vote = fx.block(3, 6, qc=fx.qc_for(fx.d(b"z"), 5))
+    n0, s0 = bad_qc_vote.qc.votes[2]
+    bad_qc_vote.qc.votes[2] = (n0, crypto.Signature(bytes([s0.flatten()[0] ^ 1]) + s0.flatten()[1:]))
+    bad_vote = messages.Vote(v.hash, 2, v.author, v.signature)
+    short_tc = fx.tc(8, hqs=((0, 3), (1, 5)))
+    outsider = messages.Vote(v.hash, 1, crypto.PublicKey(bytes(range(32))), v.signature)
+    good = bc.propose(blk_tc)
+    frames = [bc.propose(b) for b in chain + [blk_tc, bad_sig, reuse, bad_qc_vote]] + [
+        bc.vote(v), bc.vote(bad_vote), bc.vote(outsider), bc.timeout(to), bc.timeout(to_gen), bc.tc_msg(fx.tc(7)), bc.tc_msg(short_tc),
+        bc.sync_request(fx.d(b"m"), fx.pks[1]), good[:40], b"\x05\x00\x00\x00" + good[4:], b"", good + b"trailing"]
+    want = ["OK" if w is None else w for w in wire.verify_frames(frames, fx.committee, fx.e)]
+    assert want[:8] == ["OK"] * 5 + ["InvalidSignature", "AuthorityReuse", "InvalidSignature"] and want[-4:] == ["Malformed", "Malformed", "Malformed", "OK"]
+    blob = struct.pack("<I", len(fx.committee.stakes))
+    for k, st in fx.committee.stakes.items():
+        blob += k + struct.pack("<I", st)
+    blob += struct.pack("<I", len(frames)) + b"".join(struct.pack("<I", len(f)) + f for f in frames)
+    path = tmp_path / "frames.bin"
+    path.write_bytes(blob)
+    lib = build.build_engine()
+    olib = build.build_oracle()
+    exe = os.path.join(ROOT, "tests", "cpp", "frames_host_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "frames_host_test.cpp"), lib, olib,
+                           "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath," + os.path.dirname(olib)])
+    out = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split("\n")[:-1] == want, (out.stdout, want)
+    # items judged: everything except the certificates that failed a pre-check (reuse: 4 QC votes; short_tc: 2 votes; outsider: 1)
+    total = len(wire.ingest_frames(frames)["sig"])
+    assert "judged %d items" % (total - 4 - 2 - 1) in out.stderr, (out.stderr, total)
