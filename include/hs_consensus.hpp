@@ -1,6 +1,6 @@
 // hs_consensus.hpp — header-only C++ mirror of the crypto-relevant parts of consensus/src/messages.rs over the C ABI: the digest
 // layouts, the verify() pre-checks that decide what reaches the engine, and their error names (consensus/src/error.rs).
-//   Committee (config.rs:28-72), QC (messages.rs:165-208), TC (:283-315), Vote (:104-156), Timeout (:223-275).
+//   Committee (config.rs:28-72), QC (messages.rs:165-208), TC (:283-315), Vote (:104-156), Timeout (:223-275), Block (:17-90).
 // Same behaviour and error order as the reference; the signature work goes through the engine's batch front ends
 // (hs_verify_batch_shared_msg, hs_verify_qcs, hs_verify_tcs), and the receiver path — bincode frames in, one verdict per frame out —
 // through hs_ingest_consensus_frames + hs_verify_groups (verify_frames).  tests/cpp/consensus_tests.cpp ports messages_tests.rs;
@@ -218,6 +218,35 @@ struct Timeout {  // messages.rs:223-228
     e.check(hs_verify_tcs(e.raw(), &r, 1, author.bytes.data(), nullptr, f.data(), &hq, nullptr, 1, nullptr, bm), "hs_verify_tcs");
     if (!(bm[0] & 1u)) throw ConsensusError("InvalidSignature");
     if (!high_qc.is_genesis()) high_qc.verify(e, c);
+  }
+};
+
+struct Block {  // messages.rs:17-25 (crypto-relevant fields)
+  QC qc;
+  bool has_tc = false;
+  TC tc;
+  PublicKey author;
+  Round round = 0;
+  std::vector<Digest> payload;
+  Signature signature;
+  std::vector<uint8_t> preimage() const {  // Block::digest (messages.rs:79-90): author || round_le || payload digests || qc.hash
+    std::vector<uint8_t> p(32 + 8 + 32 * payload.size() + 32);
+    std::memcpy(p.data(), author.bytes.data(), 32);
+    put_le64(p.data() + 32, round);
+    for (size_t i = 0; i < payload.size(); i++) std::memcpy(p.data() + 40 + 32 * i, payload[i].bytes.data(), 32);
+    std::memcpy(p.data() + 40 + 32 * payload.size(), qc.hash.bytes.data(), 32);
+    return p;
+  }
+  void verify(const Engine &e, const Committee &c) const {  // messages.rs:54-76, same order: stake, signature, QC (unless genesis), TC
+    if (c.stake(author) == 0) throw ConsensusError("UnknownAuthority");
+    const auto pre = preimage();
+    try {
+      signature.verify(e, Digest::of(e, pre.data(), pre.size()), author);
+    } catch (const CryptoError &) {
+      throw ConsensusError("InvalidSignature");
+    }
+    if (!qc.is_genesis()) qc.verify(e, c);
+    if (has_tc) tc.verify(e, c);
   }
 };
 

@@ -7,13 +7,34 @@
 #include <cstdlib>
 #include <fstream>
 #include <iterator>
+#include <string>
 
 #include "../../include/hs_consensus.hpp"
 extern "C" {
 #include "../../oracle/hs_oracle.h"
 }
 
+// `frames_host_test --block-preimage <author hex> <round> <qc hash hex> <payload digest hex>...` prints hs::Block::preimage() as hex
+static int block_preimage(int argc, char **argv) {
+  auto unhex = [](const char *h, uint8_t *out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = (uint8_t)std::stoi(std::string(h + 2 * i, 2), nullptr, 16);
+  };
+  hs::Block b;
+  unhex(argv[2], b.author.bytes.data(), 32);
+  b.round = std::strtoull(argv[3], nullptr, 10);
+  unhex(argv[4], b.qc.hash.bytes.data(), 32);
+  for (int i = 5; i < argc; i++) {
+    hs::Digest d;
+    unhex(argv[i], d.bytes.data(), 32);
+    b.payload.push_back(d);
+  }
+  for (uint8_t x : b.preimage()) std::printf("%02x", x);
+  std::printf("\n");
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 5 && std::string(argv[1]) == "--block-preimage") return block_preimage(argc, argv);
   if (argc != 2) return 2;
   std::ifstream in(argv[1], std::ios::binary);
   std::vector<uint8_t> buf((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());

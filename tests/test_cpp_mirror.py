@@ -102,6 +102,10 @@ def test_cpp_verify_frames_host_logic_matches_the_python_mirror(oracle, golden, 
     out = subprocess.run([exe, str(path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert out.stdout.split("\n")[:-1] == want, (out.stdout, want)
+    # hs::Block::preimage (Block::digest layout, messages.rs:79-90) equals the Python mirror's, whose digest the ingest test pins to the frame bytes
+    pre = subprocess.run([exe, "--block-preimage", blk_tc.author.b.hex(), str(blk_tc.round), blk_tc.qc.hash.b.hex()] + [d.b.hex() for d in blk_tc.payload],
+                         capture_output=True, text=True)
+    assert pre.returncode == 0 and pre.stdout.strip() == blk_tc.preimage().hex()
     # items judged: everything except the certificates that failed a pre-check (reuse: 4 QC votes; short_tc: 2 votes; outsider: 1)
     total = len(wire.ingest_frames(frames)["sig"])
     assert "judged %d items" % (total - 4 - 2 - 1) in out.stderr, (out.stderr, total)
