@@ -215,3 +215,34 @@ def test_three_implementations_name_the_same_first_error(oracle, golden, tmp_pat
     got_cpp = [None if s == "OK" else s for s in out.stdout.split("\n")[:-1]]
     diff = [(i, msgs[i][0], want[i], got_cpp[i]) for i in range(len(msgs)) if want[i] != got_cpp[i]]
     assert len(got_cpp) == len(want) and not diff, diff[:5]
+
+
+def test_timeout_bursts_with_the_verified_qc_cache_match_the_sequential_restatement(oracle, golden):
+    """View-change bursts (core.rs:227): many timeouts carrying the same high_qc — or a tampered copy of it with the same (hash, round) —
+    through messages.verify_timeouts with ONE VerifiedQcCache across bursts.  The cache may only ever skip work, never change a verdict:
+    every timeout gets the error the sequential restatement names, in every burst, in any order of valid and tampered certificates."""
+    fx = sc.Fixtures(oracle, golden, sc.OracleStubEngine(oracle))
+    rng = np.random.default_rng(77)
+    ref = SequentialReference(oracle, fx.committee)
+    outsider = crypto.PublicKey(oracle.keygen(bytes([9]) * 32))
+    chain = fx.chain(4)
+    cache = messages.VerifiedQcCache(capacity=8)
+    total, hits_before = 0, 0
+    for burst in range(12):
+        ts = []
+        for _ in range(int(rng.integers(3, 40))):
+            hq = copy.deepcopy(chain[int(rng.integers(1, 4))].qc) if rng.random() < 0.9 else messages.QC.genesis()
+            t = fx.timeout(int(rng.integers(0, 4)), 50 + burst, hq)
+            if rng.random() < 0.35 and hq.votes:
+                _mutate_qc(t.high_qc, rng, outsider)          # same (hash, round) unless the round mutation hit; different bytes
+            m = int(rng.integers(0, 8))
+            if m == 0:
+                t.signature = _flip(t.signature, rng)
+            elif m == 1:
+                t.author = outsider
+            ts.append(t)
+        want = [ref.timeout(t) for t in ts]
+        got = messages.verify_timeouts(ts, fx.committee, fx.e, qc_cache=cache)
+        assert got == want, [(i, want[i], got[i]) for i in range(len(ts)) if want[i] != got[i]][:5]
+        total += len(ts)
+    assert cache.hits > 20 and total > 100      # the cache did skip repeated certificates
