@@ -146,3 +146,44 @@ def test_ingest_mutation_fuzz_under_address_sanitizer(oracle, golden, tmp_path):
     assert out.returncode == 0 and "ingest fuzz ok" in out.stdout, (out.returncode, out.stdout[-500:], out.stderr[-3000:])
     parsed = int(out.stdout.split("frames parsed")[0].split(",")[-1])
     assert parsed > 10000          # the mutations leave plenty of frames parseable: both sides of the parser are exercised
+
+
+def test_key_string_decoder_against_a_strict_base64_reference(oracle, golden):
+    """The 44-character fast path and the general path of the key decoder (crypto/src/lib.rs:103-112: base64::decode, then bytes[..32])
+    against Python's base64 with the same strictness (standard alphabet, canonical padding and trailing bits): 20 000 vote frames whose
+    author string has 0-3 characters replaced by arbitrary bytes, plus 48- and 88-character strings."""
+    import base64
+    fx = _fx(oracle, golden)
+    _, _, v, _, _ = _messages(fx)
+    vt = bc.vote(v)
+    at = 4 + 32 + 8 + 8
+    head, tail = vt[:at - 8], vt[at + 44:]
+    rng = np.random.default_rng(11)
+    alphabet = b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/="
+
+    def ref(s):
+        if len(s) % 4 or len(s) < 44:
+            return None
+        try:
+            d = base64.b64decode(s, validate=True)
+        except Exception:
+            return None
+        return d[:32] if base64.b64encode(d) == s and len(d) >= 32 else None
+
+    strings = []
+    for _ in range(20000):
+        key = rng.bytes(32 if rng.random() < 0.9 else int(rng.choice([33, 34, 35, 36, 64, 66])))
+        s = bytearray(base64.b64encode(key))
+        for _ in range(int(rng.integers(0, 4))):
+            s[int(rng.integers(0, len(s)))] = alphabet[int(rng.integers(0, 65))] if rng.random() < 0.8 else int(rng.integers(0, 256))
+        strings.append(bytes(s))
+    frames = [head + len(s).to_bytes(8, "little") + s + tail for s in strings]
+    g = wire.ingest_frames(frames)
+    want = [ref(s) for s in strings]
+    kinds = g["info"]["kind"]
+    assert [k != 255 for k in kinds] == [w is not None for w in want]
+    assert sum(w is not None for w in want) > 3000 and sum(w is None for w in want) > 3000
+    items = iter(range(len(g["pk"])))
+    for j, w in enumerate(want):
+        if w is not None:
+            assert g["pk"][next(items)].tobytes() == w, j
