@@ -10,7 +10,10 @@
 #include <map>
 #include <set>
 #include <string>
+#include <memory>
 #include <tuple>
+#include <type_traits>
+#include <unordered_map>
 
 #include "hs_crypto.hpp"
 
@@ -321,34 +324,59 @@ inline std::vector<std::string> verify_timeouts(const Engine &e, const Committee
 // all, hs_verify_groups hashes every preimage and verifies every kept item on the GPU, and the per-frame result is the error the
 // reference would have raised FIRST ("" = Ok, "Malformed" = the SerializationError the receiver logs and drops).
 // (Same host logic as hotstuff_b200/wire.py::verify_frames, which the tests hold against struct-level verification.)
+// std::vector that does not zero-fill on resize: the ingest output arrays are hundreds of megabytes for a burst of large certificates
+// and every byte the caller reads is written by hs_ingest_consensus_frames first (zero-filling them cost 3x the parsing).
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = default_init_allocator<U>;
+  };
+  using std::allocator<T>::allocator;
+  template <class U>
+  void construct(U *p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void *>(p)) U;
+  }
+  template <class U, class... Args>
+  void construct(U *p, Args &&...args) {
+    ::new (static_cast<void *>(p)) U(std::forward<Args>(args)...);
+  }
+};
+template <class T>
+using raw_vector = std::vector<T, default_init_allocator<T>>;
 struct IngestedFrames {
   std::vector<hs_frame_info> info;
-  std::vector<uint8_t> sig, pk, mode, preimages;
-  std::vector<uint32_t> msg_idx, group_idx;
-  std::vector<uint64_t> pre_off;
+  raw_vector<uint8_t> sig, pk, mode, preimages;
+  raw_vector<uint32_t> msg_idx, group_idx;
+  raw_vector<uint64_t> pre_off;
   size_t n_items() const { return msg_idx.size(); }
+  // scratch of ingest_frames (the frames laid end to end); kept so that a receiver that reuses one IngestedFrames per worker touches
+  // no fresh memory in steady state (first-touch page faults on ~300 MB per burst cost twice the parsing)
+  raw_vector<uint8_t> blob;
+  std::vector<uint64_t> off;
 };
-inline IngestedFrames ingest_frames(const std::vector<std::vector<uint8_t>> &frames) {
+// `g` is overwritten; pass the same object again to reuse its buffers.
+inline void ingest_frames(const std::vector<std::vector<uint8_t>> &frames, IngestedFrames &g) {
   const size_t n = frames.size();
-  std::vector<uint64_t> off(n + 1, 0);
-  std::vector<uint8_t> blob;
-  for (size_t i = 0; i < n; i++) {
-    blob.insert(blob.end(), frames[i].begin(), frames[i].end());
-    off[i + 1] = blob.size();
-  }
-  if (blob.empty()) blob.push_back(0);
-  IngestedFrames g;
+  std::vector<uint64_t> &off = g.off;
+  off.assign(n + 1, 0);
+  for (size_t i = 0; i < n; i++) off[i + 1] = off[i] + frames[i].size();
+  raw_vector<uint8_t> &blob = g.blob;
+  blob.resize(off[n] ? off[n] : 1);
+  for (size_t i = 0; i < n; i++)
+    if (!frames[i].empty()) std::memcpy(blob.data() + off[i], frames[i].data(), frames[i].size());
   g.info.resize(n ? n : 1);
-  // every item costs >= 116 frame bytes, every preimage is copied from frame bytes: generous first guess, exact retry on HS_ERR_NOMEM
-  size_t ci = blob.size() / 116 + n + 1, cm = blob.size() / 60 + n + 1, cp = blob.size() + 64 * n + 64;
+  // Every item costs >= 116 frame bytes; a frame holds at most 2 + (its items) preimages, 16 or 40 bytes each except the one Block
+  // preimage (72 bytes + its payload digests).  First guess from that with room for modest payloads, exact retry on HS_ERR_NOMEM.
+  size_t ci = blob.size() / 116 + n + 1, cm = ci + 2 * n + 1, cp = 16 * ci + 512 * n + 64;
   for (int attempt = 0; attempt < 2; attempt++) {
-    g.sig.assign(ci * 64, 0);
-    g.pk.assign(ci * 32, 0);
-    g.mode.assign(ci, 0);
-    g.msg_idx.assign(ci, 0);
-    g.group_idx.assign(ci, 0);
-    g.preimages.assign(cp, 0);
-    g.pre_off.assign(cm + 1, 0);
+    g.sig.resize(ci * 64);
+    g.pk.resize(ci * 32);
+    g.mode.resize(ci);
+    g.msg_idx.resize(ci);
+    g.group_idx.resize(ci);
+    g.preimages.resize(cp);
+    g.pre_off.resize(cm + 1);
     hs_ingest_out o{};
     o.cap_items = ci;
     o.cap_msgs = cm;
@@ -370,7 +398,7 @@ inline IngestedFrames ingest_frames(const std::vector<std::vector<uint8_t>> &fra
       g.preimages.resize(o.pre_bytes);
       g.pre_off.resize(o.n_msgs + 1);
       g.info.resize(n);
-      return g;
+      return;
     }
     if (rc != HS_ERR_NOMEM) throw EngineError("hs_ingest_consensus_frames: bad argument");
     ci = o.n_items + 1;
@@ -379,34 +407,66 @@ inline IngestedFrames ingest_frames(const std::vector<std::vector<uint8_t>> &fra
   }
   throw EngineError("hs_ingest_consensus_frames: capacity retry failed");
 }
+inline IngestedFrames ingest_frames(const std::vector<std::vector<uint8_t>> &frames) {
+  IngestedFrames g;
+  ingest_frames(frames, g);
+  return g;
+}
 
 // `verify_items(g) -> std::vector<bool>` judges every item of g (already reduced to the items that passed the pre-checks): the engine
 // in production (verify_frames below); the tests substitute a CPU checker to run this host logic without a GPU.
 template <class ItemVerifier>
-inline std::vector<std::string> verify_frames_with(const Committee &c, const std::vector<std::vector<uint8_t>> &frames, ItemVerifier &&verify_items) {
-  IngestedFrames g = ingest_frames(frames);
+inline std::vector<std::string> verify_frames_with(const Committee &c, const std::vector<std::vector<uint8_t>> &frames, ItemVerifier &&verify_items,
+                                                   IngestedFrames *reuse = nullptr) {
+  IngestedFrames local;
+  IngestedFrames &g = reuse ? *reuse : local;
+  ingest_frames(frames, g);
   const size_t n = frames.size(), items = g.n_items();
   std::vector<std::string> out(n), qc_err(n), tc_err(n);
   std::vector<char> skip(items, 0), decided(n, 0);
+  // Per item the reference does two ordered-map operations on 32-byte keys (HashSet insert + Committee lookup).  At hundreds of votes per
+  // certificate that, not the parsing, bounds the host side (measured: tools/frames_bench.cpp), so: one hash index over the committee
+  // per call (keys are curve points — their first 8 bytes are hash enough) and, for the duplicate check, a per-validator stamp that
+  // holds the number of the last certificate the validator appeared in.
+  struct member {
+    Stake stake;
+    uint32_t slot;
+  };
+  struct key_hash {
+    size_t operator()(const std::array<uint8_t, 32> &k) const {
+      uint64_t h;
+      std::memcpy(&h, k.data(), 8);
+      return (size_t)(h * 0x9E3779B97F4A7C15ull);
+    }
+  };
+  std::unordered_map<std::array<uint8_t, 32>, member, key_hash> index;
+  index.reserve(c.stakes.size() * 2);
+  for (auto &kv : c.stakes) index.emplace(kv.first, member{kv.second, (uint32_t)index.size()});
+  const Stake threshold = c.quorum_threshold();
+  std::vector<uint32_t> stamp(index.size(), 0);
+  uint32_t certificate = 0;
   auto key_of = [&](size_t i) {
     std::array<uint8_t, 32> k;
     std::memcpy(k.data(), g.pk.data() + i * 32, 32);
     return k;
   };
   auto stake_of = [&](size_t i) {
-    auto it = c.stakes.find(key_of(i));
-    return it == c.stakes.end() ? (Stake)0 : it->second;
+    auto it = index.find(key_of(i));
+    return it == index.end() ? (Stake)0 : it->second.stake;
   };
   auto quorum = [&](uint32_t lo, uint32_t hi, const char *err) -> std::string {  // messages.rs:182-194 / :292-304
     Stake weight = 0;
-    std::set<std::array<uint8_t, 32>> used;
+    certificate++;
     for (uint32_t i = lo; i < hi; i++) {
-      if (!used.insert(key_of(i)).second) return "AuthorityReuse";
-      const Stake st = stake_of(i);
-      if (st == 0) return "UnknownAuthority";
-      weight += st;
+      auto it = index.find(key_of(i));
+      // (a key without stake is never inserted into `used` by the reference — its first appearance already fails — so for it the reuse
+      // check that precedes the stake check can never fire)
+      if (it == index.end() || it->second.stake == 0) return "UnknownAuthority";
+      if (stamp[it->second.slot] == certificate) return "AuthorityReuse";
+      stamp[it->second.slot] = certificate;
+      weight += it->second.stake;
     }
-    return weight >= c.quorum_threshold() ? "" : err;
+    return weight >= threshold ? "" : err;
   };
   auto skip_range = [&](uint32_t lo, uint32_t hi) {
     for (uint32_t i = lo; i < hi; i++) skip[i] = 1;
@@ -438,26 +498,42 @@ inline std::vector<std::string> verify_frames_with(const Committee &c, const std
       if (!tc_err[j].empty()) skip_range(f.tc_lo, f.tc_hi);
     }
   }
-  // one pass over the items that are still to be judged
-  IngestedFrames kept;
-  std::vector<size_t> kept_of;
-  for (size_t i = 0; i < items; i++) {
-    if (skip[i]) continue;
-    kept_of.push_back(i);
-    kept.sig.insert(kept.sig.end(), g.sig.begin() + i * 64, g.sig.begin() + (i + 1) * 64);
-    kept.pk.insert(kept.pk.end(), g.pk.begin() + i * 32, g.pk.begin() + (i + 1) * 32);
-    kept.mode.push_back(g.mode[i]);
-    kept.msg_idx.push_back(g.msg_idx[i]);
-    kept.group_idx.push_back(g.group_idx[i]);
-  }
-  kept.preimages = g.preimages;
-  kept.pre_off = g.pre_off;
-  kept.info = g.info;
+  // one pass over the items that are still to be judged (normally all of them: then the ingest arrays go to the engine as they are)
   std::vector<char> ok(items, 0);
-  if (!kept_of.empty()) {
+  size_t n_skip = 0;
+  for (size_t i = 0; i < items; i++) n_skip += skip[i] ? 1 : 0;
+  if (n_skip == 0) {
+    if (items) {
+      const std::vector<bool> got = verify_items(g);
+      if (got.size() != items) throw EngineError("verify_frames: item verifier returned the wrong number of verdicts");
+      for (size_t i = 0; i < items; i++) ok[i] = got[i] ? 1 : 0;
+    }
+  } else if (n_skip < items) {
+    IngestedFrames kept;
+    std::vector<size_t> kept_of;
+    const size_t nk = items - n_skip;
+    kept_of.reserve(nk);
+    kept.sig.resize(nk * 64);
+    kept.pk.resize(nk * 32);
+    kept.mode.resize(nk);
+    kept.msg_idx.resize(nk);
+    kept.group_idx.resize(nk);
+    for (size_t i = 0; i < items; i++) {
+      if (skip[i]) continue;
+      const size_t k = kept_of.size();
+      kept_of.push_back(i);
+      std::memcpy(kept.sig.data() + k * 64, g.sig.data() + i * 64, 64);
+      std::memcpy(kept.pk.data() + k * 32, g.pk.data() + i * 32, 32);
+      kept.mode[k] = g.mode[i];
+      kept.msg_idx[k] = g.msg_idx[i];
+      kept.group_idx[k] = g.group_idx[i];
+    }
+    kept.preimages = g.preimages;
+    kept.pre_off = g.pre_off;
+    kept.info = g.info;
     const std::vector<bool> got = verify_items(kept);
-    if (got.size() != kept_of.size()) throw EngineError("verify_frames: item verifier returned the wrong number of verdicts");
-    for (size_t k = 0; k < kept_of.size(); k++) ok[kept_of[k]] = got[k] ? 1 : 0;
+    if (got.size() != nk) throw EngineError("verify_frames: item verifier returned the wrong number of verdicts");
+    for (size_t k = 0; k < nk; k++) ok[kept_of[k]] = got[k] ? 1 : 0;
   }
   auto all_ok = [&](uint32_t lo, uint32_t hi) {
     for (uint32_t i = lo; i < hi; i++)
@@ -475,7 +551,8 @@ inline std::vector<std::string> verify_frames_with(const Committee &c, const std
   }
   return out;
 }
-inline std::vector<std::string> verify_frames(const Engine &e, const Committee &c, const std::vector<std::vector<uint8_t>> &frames) {
+inline std::vector<std::string> verify_frames(const Engine &e, const Committee &c, const std::vector<std::vector<uint8_t>> &frames,
+                                              IngestedFrames *reuse = nullptr) {
   return verify_frames_with(c, frames, [&](const IngestedFrames &k) {
     const size_t ni = k.n_items(), ng = k.info.size();
     std::vector<uint32_t> item_bits((ni + 31) / 32 + 1, 0), group_bits((ng + 31) / 32 + 1, 0);
@@ -485,7 +562,7 @@ inline std::vector<std::string> verify_frames(const Engine &e, const Committee &
     std::vector<bool> got(ni);
     for (size_t i = 0; i < ni; i++) got[i] = (item_bits[i / 32] >> (i % 32)) & 1u;
     return got;
-  });
+  }, reuse);
 }
 
 }  // namespace hs
