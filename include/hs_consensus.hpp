@@ -49,6 +49,62 @@ inline void put_le64(uint8_t *p, uint64_t v) {
   for (int i = 0; i < 8; i++) p[i] = (uint8_t)(v >> (8 * i));
 }
 
+// Per-batch acceleration of the stake / duplicate / quorum pre-checks (messages.rs:182-194, :292-304).  Per vote the reference does a
+// HashSet insert and a Committee lookup on 32-byte keys; with ordered containers that costs more host time than the GPU needs for the
+// signatures once certificates carry hundreds of votes (measured: tools/frames_bench.cpp).  One hash index over the committee per batch
+// (keys are curve points: their first 8 bytes are hash enough) and a per-validator stamp holding the number of the last certificate the
+// validator appeared in give the same answers in O(1) per vote.
+class CommitteeIndex {
+ public:
+  explicit CommitteeIndex(const Committee &c) : threshold_(c.quorum_threshold()) {
+    index_.reserve(c.stakes.size() * 2);
+    for (auto &kv : c.stakes) index_.emplace(kv.first, member{kv.second, (uint32_t)index_.size()});
+    stamp_.assign(index_.size(), 0);
+  }
+  Stake stake(const uint8_t key[32]) const {
+    auto it = index_.find(load(key));
+    return it == index_.end() ? (Stake)0 : it->second.stake;
+  }
+  // The ConsensusError name the reference raises first for a certificate of `n` votes whose i-th key is key_of(i), or nullptr.
+  // (A key without stake is never inserted into the reference's `used` set — its first appearance already fails — so for it the reuse
+  // check that precedes the stake check can never fire.)
+  template <class KeyOf>
+  const char *certificate_error(size_t n, KeyOf &&key_of, const char *quorum_error) {
+    Stake weight = 0;
+    certificate_++;
+    for (size_t i = 0; i < n; i++) {
+      auto it = index_.find(load(key_of(i)));
+      if (it == index_.end() || it->second.stake == 0) return "UnknownAuthority";
+      if (stamp_[it->second.slot] == certificate_) return "AuthorityReuse";
+      stamp_[it->second.slot] = certificate_;
+      weight += it->second.stake;
+    }
+    return weight >= threshold_ ? nullptr : quorum_error;
+  }
+
+ private:
+  struct member {
+    Stake stake;
+    uint32_t slot;
+  };
+  struct key_hash {
+    size_t operator()(const std::array<uint8_t, 32> &k) const {
+      uint64_t h;
+      std::memcpy(&h, k.data(), 8);
+      return (size_t)(h * 0x9E3779B97F4A7C15ull);
+    }
+  };
+  static std::array<uint8_t, 32> load(const uint8_t *p) {
+    std::array<uint8_t, 32> k;
+    std::memcpy(k.data(), p, 32);
+    return k;
+  }
+  std::unordered_map<std::array<uint8_t, 32>, member, key_hash> index_;
+  std::vector<uint32_t> stamp_;
+  uint32_t certificate_ = 0;
+  Stake threshold_;
+};
+
 struct QC {  // messages.rs:165-169
   Digest hash;
   Round round = 0;
@@ -84,20 +140,29 @@ struct QC {  // messages.rs:165-169
 };
 
 // Many QCs in ONE engine call (the view-change burst, core.rs:227): pre-checks on the host, digests + votes + per-QC AND on the GPU.
-inline std::vector<bool> verify_qcs(const Engine &e, const Committee &c, const std::vector<QC> &qcs) {
+// `verify_votes(pre /* 40 B per live QC */, n_live, pk, sig, qi /* live QC of vote i */, n_votes) -> std::vector<bool>` (one verdict per live
+// QC) is the engine in production (verify_qcs below); the tests substitute a CPU checker to run this host logic without a GPU.
+template <class VoteVerifier>
+inline std::vector<bool> verify_qcs_with(const Committee &c, const std::vector<QC> &qcs, VoteVerifier &&verify_votes) {
   std::vector<bool> ok(qcs.size(), true);
+  size_t total = 0;
+  for (auto &q : qcs) total += q.votes.size();
   std::vector<uint8_t> pre, pk, sig;
   std::vector<uint32_t> qi, live;
+  pre.reserve(qcs.size() * 40);
+  pk.reserve(total * 32);
+  sig.reserve(total * 64);
+  qi.reserve(total);
+  CommitteeIndex index(c);
   for (size_t j = 0; j < qcs.size(); j++) {
-    try {
-      qcs[j].check_quorum(c);
-    } catch (const ConsensusError &) {
-      ok[j] = false;
+    const QC &q = qcs[j];
+    if (index.certificate_error(q.votes.size(), [&](size_t i) { return q.votes[i].first.bytes.data(); }, "QCRequiresQuorum")) {
+      ok[j] = false;  // same outcome as QC::check_quorum (messages.rs:182-194): rejected before any crypto
       continue;
     }
-    const auto p = qcs[j].preimage();
+    const auto p = q.preimage();
     pre.insert(pre.end(), p.begin(), p.end());
-    for (auto &v : qcs[j].votes) {
+    for (auto &v : q.votes) {
       pk.insert(pk.end(), v.first.bytes.begin(), v.first.bytes.end());
       const auto f = v.second.flatten();
       sig.insert(sig.end(), f.begin(), f.end());
@@ -106,10 +171,19 @@ inline std::vector<bool> verify_qcs(const Engine &e, const Committee &c, const s
     live.push_back((uint32_t)j);
   }
   if (live.empty()) return ok;
-  std::vector<uint32_t> bm((live.size() + 31) / 32 + 1);
-  e.check(hs_verify_qcs(e.raw(), pre.data(), live.size(), pk.data(), nullptr, sig.data(), qi.data(), qi.size(), nullptr, bm.data()), "hs_verify_qcs");
-  for (size_t k = 0; k < live.size(); k++) ok[live[k]] = (bm[k / 32] >> (k % 32)) & 1u;
+  const std::vector<bool> got = verify_votes(pre.data(), live.size(), pk.data(), sig.data(), qi.data(), qi.size());
+  if (got.size() != live.size()) throw EngineError("verify_qcs: vote verifier returned the wrong number of verdicts");
+  for (size_t k = 0; k < live.size(); k++) ok[live[k]] = got[k];
   return ok;
+}
+inline std::vector<bool> verify_qcs(const Engine &e, const Committee &c, const std::vector<QC> &qcs) {
+  return verify_qcs_with(c, qcs, [&](const uint8_t *pre, size_t n_live, const uint8_t *pk, const uint8_t *sig, const uint32_t *qi, size_t n_votes) {
+    std::vector<uint32_t> bm((n_live + 31) / 32 + 1);
+    e.check(hs_verify_qcs(e.raw(), pre, n_live, pk, nullptr, sig, qi, n_votes, nullptr, bm.data()), "hs_verify_qcs");
+    std::vector<bool> got(n_live);
+    for (size_t k = 0; k < n_live; k++) got[k] = (bm[k / 32] >> (k % 32)) & 1u;
+    return got;
+  });
 }
 
 // Verified-QC cache: during a view change every Timeout carries its sender's high_qc, so a node re-verifies the same
@@ -424,49 +498,11 @@ inline std::vector<std::string> verify_frames_with(const Committee &c, const std
   const size_t n = frames.size(), items = g.n_items();
   std::vector<std::string> out(n), qc_err(n), tc_err(n);
   std::vector<char> skip(items, 0), decided(n, 0);
-  // Per item the reference does two ordered-map operations on 32-byte keys (HashSet insert + Committee lookup).  At hundreds of votes per
-  // certificate that, not the parsing, bounds the host side (measured: tools/frames_bench.cpp), so: one hash index over the committee
-  // per call (keys are curve points — their first 8 bytes are hash enough) and, for the duplicate check, a per-validator stamp that
-  // holds the number of the last certificate the validator appeared in.
-  struct member {
-    Stake stake;
-    uint32_t slot;
-  };
-  struct key_hash {
-    size_t operator()(const std::array<uint8_t, 32> &k) const {
-      uint64_t h;
-      std::memcpy(&h, k.data(), 8);
-      return (size_t)(h * 0x9E3779B97F4A7C15ull);
-    }
-  };
-  std::unordered_map<std::array<uint8_t, 32>, member, key_hash> index;
-  index.reserve(c.stakes.size() * 2);
-  for (auto &kv : c.stakes) index.emplace(kv.first, member{kv.second, (uint32_t)index.size()});
-  const Stake threshold = c.quorum_threshold();
-  std::vector<uint32_t> stamp(index.size(), 0);
-  uint32_t certificate = 0;
-  auto key_of = [&](size_t i) {
-    std::array<uint8_t, 32> k;
-    std::memcpy(k.data(), g.pk.data() + i * 32, 32);
-    return k;
-  };
-  auto stake_of = [&](size_t i) {
-    auto it = index.find(key_of(i));
-    return it == index.end() ? (Stake)0 : it->second.stake;
-  };
+  CommitteeIndex index(c);
+  auto stake_of = [&](size_t i) { return index.stake(g.pk.data() + i * 32); };
   auto quorum = [&](uint32_t lo, uint32_t hi, const char *err) -> std::string {  // messages.rs:182-194 / :292-304
-    Stake weight = 0;
-    certificate++;
-    for (uint32_t i = lo; i < hi; i++) {
-      auto it = index.find(key_of(i));
-      // (a key without stake is never inserted into `used` by the reference — its first appearance already fails — so for it the reuse
-      // check that precedes the stake check can never fire)
-      if (it == index.end() || it->second.stake == 0) return "UnknownAuthority";
-      if (stamp[it->second.slot] == certificate) return "AuthorityReuse";
-      stamp[it->second.slot] = certificate;
-      weight += it->second.stake;
-    }
-    return weight >= threshold ? "" : err;
+    const char *e = index.certificate_error(hi - lo, [&](size_t i) { return g.pk.data() + (lo + i) * 32; }, err);
+    return e ? e : "";
   };
   auto skip_range = [&](uint32_t lo, uint32_t hi) {
     for (uint32_t i = lo; i < hi; i++) skip[i] = 1;

@@ -215,6 +215,17 @@ def test_three_implementations_name_the_same_first_error(oracle, golden, tmp_pat
     got_cpp = [None if s == "OK" else s for s in out.stdout.split("\n")[:-1]]
     diff = [(i, msgs[i][0], want[i], got_cpp[i]) for i in range(len(msgs)) if want[i] != got_cpp[i]]
     assert len(got_cpp) == len(want) and not diff, diff[:5]
+    # the struct-level batch front end (hs::verify_qcs_with: CommitteeIndex pre-checks + one grouped call) on every embedded certificate
+    out = subprocess.run([exe, "--qcs", str(path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    got_qc = out.stdout.split("\n")[:-1]
+    want_qc = []
+    for kind, m, _ in msgs:
+        q = m.qc if kind == "block" else m.high_qc if kind == "timeout" else None
+        # (a certificate that equals genesis — hash and round zero — is never verified upstream and carries no items)
+        want_qc.append("-" if q is None or not q.votes or q == messages.QC.genesis() else ("OK" if ref.qc(q) is None else "BAD"))
+    assert got_qc == want_qc, [(i, want_qc[i], got_qc[i]) for i in range(len(msgs)) if want_qc[i] != got_qc[i]][:5]
+    assert want_qc.count("OK") > 100 and want_qc.count("BAD") > 100
 
 
 def test_timeout_bursts_with_the_verified_qc_cache_match_the_sequential_restatement(oracle, golden):
