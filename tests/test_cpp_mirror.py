@@ -23,26 +23,15 @@ def test_cpp_mirror_compiles_and_links():
     assert os.path.exists(_build("consensus_tests"))
 
 
-@pytest.mark.gpu
-def test_cpp_port_of_reference_crypto_tests(oracle, golden):
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
+def _crypto_args(oracle, golden):
     r = golden["reference"]
     seeds = [bytes.fromhex(s) for s in r["seeds"]]
     hello = bytes.fromhex(r["hello_digest"])
-    args = [r["hello_digest"], r["bad_digest"], r["hello_sig_key3"], r["pks"][3], r["pks"][2], r["pks"][1],
+    return [r["hello_digest"], r["bad_digest"], r["hello_sig_key3"], r["pks"][3], r["pks"][2], r["pks"][1],
             oracle.sign(seeds[2], hello).hex(), oracle.sign(seeds[1], hello).hex(), r["serialized_batch"], r["batch_digest"]]
-    out = subprocess.run([_build()] + args, capture_output=True, text=True)
-    assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stderr
 
 
-@pytest.mark.gpu
-def test_cpp_port_of_reference_messages_tests(oracle, golden):
-    """include/hs_consensus.hpp against consensus/src/tests/messages_tests.rs (QC cases) + Vote / Timeout / TC, compiled C++."""
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
+def _consensus_args(oracle, golden):
     r = golden["reference"]
     seeds = [bytes.fromhex(s) for s in r["seeds"]]
     args = list(r["pks"])
@@ -53,7 +42,45 @@ def test_cpp_port_of_reference_messages_tests(oracle, golden):
     args += [oracle.sign(seeds[2], oracle.digest32((9).to_bytes(8, "little") + (1).to_bytes(8, "little"))).hex()]
     for i, hq in ((0, 3), (1, 5), (2, 4)):
         args.append(oracle.sign(seeds[i], oracle.digest32((7).to_bytes(8, "little") + hq.to_bytes(8, "little"))).hex())
-    out = subprocess.run([_build("consensus_tests")] + args, capture_output=True, text=True)
+    return args
+
+
+@pytest.mark.gpu
+def test_cpp_port_of_reference_crypto_tests(oracle, golden):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = subprocess.run([_build()] + _crypto_args(oracle, golden), capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_port_of_reference_messages_tests(oracle, golden):
+    """include/hs_consensus.hpp against consensus/src/tests/messages_tests.rs (QC cases) + Vote / Timeout / TC, compiled C++."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = subprocess.run([_build("consensus_tests")] + _consensus_args(oracle, golden), capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp consensus mirror ok" in out.stdout, out.stderr + out.stdout
+
+
+def _build_on_stub(name):
+    """The same test source linked against tests/cpp/stub_abi.cpp (the C ABI subset answered by the CPU oracle) instead of libhs_crypto.so."""
+    from hotstuff_b200 import build
+    olib = build.build_oracle()
+    out = os.path.join(ROOT, "tests", "cpp", name + "_stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", out, os.path.join(ROOT, "tests", "cpp", name + ".cpp"), os.path.join(ROOT, "tests", "cpp", "stub_abi.cpp"),
+                           os.path.join(ROOT, "hotstuff_b200", "csrc", "hs_ingest.cpp"), olib, "-Wl,-rpath," + os.path.dirname(olib)])
+    return out
+
+
+def test_cpp_ports_of_the_reference_tests_run_on_the_oracle_stub(oracle, golden):
+    """The host logic of the compiled mirror (types, digest layouts, pre-checks, error names, batching, the verified-QC cache) does not
+    need a GPU to be wrong: the C++ ports of crypto_tests.rs and messages_tests.rs also run here, with the engine's entry points answered
+    by the oracle.  (On a GPU box the same sources run against the CUDA engine.)"""
+    out = subprocess.run([_build_on_stub("crypto_tests")] + _crypto_args(oracle, golden), capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp mirror ok" in out.stdout, out.stderr + out.stdout
+    out = subprocess.run([_build_on_stub("consensus_tests")] + _consensus_args(oracle, golden), capture_output=True, text=True)
     assert out.returncode == 0 and "cpp consensus mirror ok" in out.stdout, out.stderr + out.stdout
 
 

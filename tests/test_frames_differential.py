@@ -215,6 +215,14 @@ def test_three_implementations_name_the_same_first_error(oracle, golden, tmp_pat
     got_cpp = [None if s == "OK" else s for s in out.stdout.split("\n")[:-1]]
     diff = [(i, msgs[i][0], want[i], got_cpp[i]) for i in range(len(msgs)) if want[i] != got_cpp[i]]
     assert len(got_cpp) == len(want) and not diff, diff[:5]
+    # the production wrapper hs::verify_frames(Engine, ...) -> hs_verify_groups, with the engine's entry points answered by the oracle stub
+    exe2 = os.path.join(ROOT, "tests", "cpp", "frames_engine_path_stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-DHS_TEST_ENGINE_PATH", "-o", exe2, os.path.join(ROOT, "tests", "cpp", "frames_host_test.cpp"),
+                           os.path.join(ROOT, "tests", "cpp", "stub_abi.cpp"), os.path.join(ROOT, "hotstuff_b200", "csrc", "hs_ingest.cpp"), olib,
+                           "-Wl,-rpath," + os.path.dirname(olib)])
+    out = subprocess.run([exe2, str(path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert [None if s == "OK" else s for s in out.stdout.split("\n")[:-1]] == want
     # the struct-level batch front end (hs::verify_qcs_with: CommitteeIndex pre-checks + one grouped call) on every embedded certificate
     out = subprocess.run([exe, "--qcs", str(path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
